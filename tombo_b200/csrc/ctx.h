@@ -1,0 +1,78 @@
+// ctx.h -- host-side context shared by the translation units of libtombo_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/tombo_b200.h"
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    // grow-only device buffer
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    template <class T> T *as() { return (T *)p; }
+};
+
+struct tb2_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double last_ms_total = 0, last_ms_dp = 0, last_dp_launches = 0;
+    // model tables
+    DevBuf model_means, model_sds, alt_means;
+    int kmer_width = 0, central_pos = 0, alt_kmer_width = 0;
+    // generic scratch pool (named slots), grow-only
+    std::vector<DevBuf> pool = std::vector<DevBuf>(64);
+    // pinned host staging for small results
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+#define TB2_CUDA_TRY(ctx, expr)                                                        \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            char _b[512];                                                              \
+            snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,     \
+                     cudaGetErrorString(_e));                                          \
+            (ctx)->err = _b;                                                           \
+            cudaGetLastError();                                                        \
+            return TB2_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+#define TB2_CHECK_LAUNCH(ctx)                                                          \
+    do {                                                                               \
+        (ctx)->launches++;                                                             \
+        TB2_CUDA_TRY(ctx, cudaGetLastError());                                         \
+    } while (0)
+
+static inline int tb2_use(tb2_ctx *ctx)
+{
+    if (!ctx) return TB2_ERR_INVALID_ARG;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return TB2_ERR_CUDA; }
+    return TB2_OK;
+}

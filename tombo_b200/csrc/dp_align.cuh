@@ -1,0 +1,287 @@
+// dp_align.cuh -- event -> sequence assignment of one read by one warp:
+// find_adaptive_base_assignment (resquiggle.py:866-1050, start_clip_bases=None)
+// with find_seq_start_in_events (:685-752), _get_masked_start_fwd_pass (:607-683),
+// find_static_base_assignment (:547-600), c_adaptive_banded_forward_pass,
+// c_banded_traceback, _trim_traceback (:754-764), get_rel_raw_coords (:858-864).
+#pragma once
+#include "dp_row.cuh"
+
+#define TB2_MAX_WPL 5  // band widths up to 5*16*32 = 2560 cells
+#define TB2_MASK_FILL_Z_SCORE (-15.0)
+
+// per-warp resources
+struct WarpRes {
+    double *smem_rows;    // 2 * smem_cap doubles
+    int smem_cap;         // cells per row buffer available in shared memory
+    double *grow;         // optional global row scratch, 2 * grow_cap doubles
+    int grow_cap;
+    uint32_t *tb;         // packed move scratch
+    size_t tb_words;      // capacity in words
+};
+
+// one read's view
+struct AlignRead {
+    const int *cpts;      // valid changepoints (n_cpts)
+    int n_cpts;
+    const double *em;     // event means (n_cpts - 1)
+    const double *rm, *rs;  // reference levels (nb)
+    int nb;
+    int *starts;          // scratch, nb ints
+    int *read_tb;         // scratch, nb + 1 ints
+    int *segs;            // out, nb + 1
+    int *rsrtr;           // out
+    int *dbg;             // out (may be null): path, mapped_start, clip
+};
+
+__device__ __forceinline__ bool tb2_setup_geom(PassCtx &pc, const WarpRes &wr, int W)
+{
+    pc.W = W;
+    pc.chunk = (W + 31) / 32;
+    const int cells = pc.chunk * 32;
+    if (cells <= wr.smem_cap) {
+        pc.buf0 = wr.smem_rows;
+        pc.buf1 = wr.smem_rows + wr.smem_cap;
+        return true;
+    }
+    if (wr.grow != nullptr && cells <= wr.grow_cap) {
+        pc.buf0 = wr.grow;
+        pc.buf1 = wr.grow + wr.grow_cap;
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ int tb2_wpl_of(int chunk) { return (chunk + 15) / 16; }
+
+__device__ int tb2_run_rows_dyn(int wpl, const PassCtx &pc, const DpConsts &c, int mode,
+                                int r_begin, int r_end, int nb_total, int *cur_sel, int *amax)
+{
+    switch (wpl) {
+    case 1: return tb2_run_rows<1>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
+    case 2: return tb2_run_rows<2>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
+    case 3: return tb2_run_rows<3>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
+    case 4: return tb2_run_rows<4>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
+    case 5: return tb2_run_rows<5>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
+    default: return TB2_ERR_CAPACITY;
+    }
+}
+
+__device__ int tb2_traceback_dyn(int wpl, const uint32_t *tb, const int *starts, int nb, int W,
+                                 int chunk, int band_pos, int thresh, int *read_tb)
+{
+    switch (wpl) {
+    case 1: return tb2_traceback<1>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    case 2: return tb2_traceback<2>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    case 3: return tb2_traceback<3>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    case 4: return tb2_traceback<4>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    case 5: return tb2_traceback<5>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    default: return TB2_ERR_CAPACITY;
+    }
+}
+
+__device__ __forceinline__ void tb2_pc_defaults(PassCtx &pc, const AlignRead &a,
+                                                const WarpRes &wr, const DpConsts &c)
+{
+    pc.em = a.em; pc.n_em = a.n_cpts - 1;
+    pc.rm = a.rm; pc.rs_ = a.rs; pc.zmat = nullptr;
+    pc.mso = 0; pc.msp_start = 0; pc.msp_stop = 0;
+    pc.mask_fill = TB2_MASK_FILL_Z_SCORE;
+    pc.mask_shifted = (TB2_MASK_FILL_Z_SCORE - c.z_shift) + c.z_shift;  // resquiggle.py:666,678
+    pc.starts = a.starts; pc.tb = wr.tb; pc.dbg_fwd = nullptr; pc.dbg_tb = nullptr;
+}
+
+// find_seq_start_in_events resquiggle.py:685-752
+__device__ int tb2_start_find(const AlignRead &a, const WarpRes &wr, const DpConsts &c,
+                              int num_bases, int num_events, bool check_score,
+                              double sig_match_thresh, int *start_loc, double *epb)
+{
+    const int lane = tb2_lane();
+    const int n_em = a.n_cpts - 1;
+    if (n_em < num_events + num_bases) return TB2_ERR_READ_TOO_SHORT_START;
+    if (a.nb < num_bases) return TB2_ERR_MAP_TOO_SHORT_START;
+    PassCtx pc;
+    tb2_pc_defaults(pc, a, wr, c);
+    if (!tb2_setup_geom(pc, wr, num_events)) return TB2_ERR_CAPACITY;
+    const int wpl = tb2_wpl_of(pc.chunk);
+    if (wpl > TB2_MAX_WPL || (size_t)num_bases * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
+    if (num_bases + 1 > pc.chunk * 32) return TB2_ERR_CAPACITY;  // scoring scratch
+    for (int r = lane; r < num_bases; r += 32) a.starts[r] = r;  // :721
+    __syncwarp();
+    int sel, amax = 0;
+    tb2_init_row0(pc, &sel);
+    int st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_PLAIN, 0, num_bases, num_bases, &sel, &amax);
+    if (st != TB2_OK) return st;
+    st = tb2_traceback_dyn(wpl, wr.tb, a.starts, num_bases, pc.W, pc.chunk, amax, -1, a.read_tb);
+    if (st != TB2_OK) return st;
+    int sloc = 0;
+    double e = 0;
+    if (lane == 0) {
+        sloc = a.read_tb[0];
+        e = (double)(a.read_tb[num_bases] - a.read_tb[0]) / (double)(num_bases + 1);  // :749
+        if (check_score) {
+            // score_valid_bases tombo_stats.py:2340-2362 (np.mean = pairwise sum / n)
+            double *t = pc.buf0;
+            int nv = 0;
+            for (int i = 0; i < num_bases; ++i) {
+                const int s0 = a.read_tb[i], s1 = a.read_tb[i + 1];
+                if (s1 != s0) {
+                    const double m = tb2_pairwise_sum(a.em + s0, s1 - s0) / (double)(s1 - s0);
+                    t[nv++] = fabs((m - a.rm[i]) / a.rs[i]);
+                }
+            }
+            if (nv == 0) st = TB2_ERR_INVALID_START_PATH;
+            else if (tb2_pairwise_sum(t, nv) / (double)nv > sig_match_thresh)
+                st = TB2_ERR_POOR_START_MATCH;
+        }
+    }
+    st = __shfl_sync(TB2_FULL_MASK, st, 0);
+    *start_loc = __shfl_sync(TB2_FULL_MASK, sloc, 0);
+    *epb = __shfl_sync(TB2_FULL_MASK, e, 0);
+    __syncwarp();
+    return st;
+}
+
+// cpts[read_tb] - cpts[read_tb[0]]  (get_rel_raw_coords resquiggle.py:858-864)
+__device__ int tb2_emit_segs(const AlignRead &a, const int *cpts, int n_idx)
+{
+    const int lane = tb2_lane();
+    const int nb = a.nb;
+    int bad = 0;
+    const int t0 = a.read_tb[0];
+    const int base = (t0 >= 0 && t0 < n_idx) ? cpts[t0] : 0;
+    for (int i = lane; i <= nb; i += 32) {
+        const int t = a.read_tb[i];
+        if (t < 0 || t >= n_idx) { bad = 1; continue; }
+        a.segs[i] = cpts[t] - base;
+    }
+    if (__any_sync(TB2_FULL_MASK, bad) || t0 < 0 || t0 >= n_idx) return TB2_ERR_UNEXPECTED;
+    if (lane == 0) *a.rsrtr = base;
+    return TB2_OK;
+}
+
+// find_static_base_assignment resquiggle.py:547-600 + get_short_read_results
+__device__ int tb2_static_assign(const AlignRead &a, const WarpRes &wr, const DpConsts &c)
+{
+    const int lane = tb2_lane();
+    const int n_em = a.n_cpts - 1, nb = a.nb;
+    const int mask_len = min(nb, n_em) / 4;
+    const int W = n_em - mask_len;
+    if (W <= 0 || nb <= 0) return TB2_ERR_UNEXPECTED;
+    PassCtx pc;
+    tb2_pc_defaults(pc, a, wr, c);
+    if (!tb2_setup_geom(pc, wr, W)) return TB2_ERR_CAPACITY;
+    const int wpl = tb2_wpl_of(pc.chunk);
+    if (wpl > TB2_MAX_WPL || (size_t)nb * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
+    const int n0 = nb - 2 * mask_len;
+    for (int r = lane; r < nb; r += 32)   // :567-569
+        a.starts[r] = (r < n0) ? 0
+                               : (int)tb2_linspace_at(0.0, (double)mask_len, 2 * mask_len, r - n0);
+    __syncwarp();
+    int sel, amax = 0;
+    tb2_init_row0(pc, &sel);
+    int st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_PLAIN, 0, nb, nb, &sel, &amax);
+    if (st != TB2_OK) return st;
+    st = tb2_traceback_dyn(wpl, wr.tb, a.starts, nb, pc.W, pc.chunk, amax, -1, a.read_tb);
+    if (st != TB2_OK) return st;
+    return tb2_emit_segs(a, a.cpts, a.n_cpts);
+}
+
+__device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_params &p,
+                              double sig_match_thresh)
+{
+    const int lane = tb2_lane();
+    DpConsts c;
+    c.z_shift = p.z_shift; c.stay_pen = p.stay_pen; c.skip_pen = p.skip_pen;
+    c.winsor = !isnan(p.max_half_z_score);
+    c.mhz = c.winsor ? p.max_half_z_score : 0.0;
+    const int n_em = a.n_cpts - 1, nb = a.nb;
+    if (n_em < 1 || nb < 1) return TB2_ERR_UNEXPECTED;
+    const int start_bw = (int)p.start_bw, start_save_bw = (int)p.start_save_bw,
+              start_n = (int)p.start_n_bases, bw = (int)p.bandwidth;
+    if (a.dbg && lane == 0) { a.dbg[0] = 0; a.dbg[1] = -1; a.dbg[2] = -1; }
+    // short reads: one static band over the whole read (:986-989)
+    if (n_em < start_bw + start_n || nb < start_n) return tb2_static_assign(a, wr, c);
+    int mapped_start = 0;
+    double epb = 0;
+    int st = tb2_start_find(a, wr, c, start_n, start_bw, true, sig_match_thresh, &mapped_start,
+                            &epb);
+    if (st != TB2_OK && st != TB2_ERR_UNEXPECTED && st != TB2_ERR_CAPACITY) {  // except TomboError
+        if (n_em < start_save_bw + start_n) return tb2_static_assign(a, wr, c);
+        st = tb2_start_find(a, wr, c, start_n, start_save_bw, false, 0.0, &mapped_start, &epb);
+    }
+    if (st != TB2_OK) return st;
+    if (epb == 0) return TB2_ERR_OPEN_PORE;  // :1008
+    const int half_bw = bw / 2;
+    int clip, mso;
+    if (mapped_start < half_bw) { clip = 0; mso = mapped_start; }
+    else { clip = mapped_start - half_bw; mso = half_bw; }
+    if (a.dbg && lane == 0) { a.dbg[1] = mapped_start; a.dbg[2] = clip; }
+    if ((int)((double)(half_bw + 1) / epb) >= nb || (n_em - mso - clip < bw))  // :1024-1027
+        return tb2_static_assign(a, wr, c);
+    if (a.dbg && lane == 0) a.dbg[0] = 1;
+
+    // ---- _get_masked_start_fwd_pass :607-683 ----
+    const int n_emc = n_em - clip;
+    if (n_emc - mso < bw) return TB2_ERR_START_TOO_FAR;
+    PassCtx pc;
+    tb2_pc_defaults(pc, a, wr, c);
+    pc.em = a.em + clip; pc.n_em = n_emc; pc.mso = mso;
+    if (!tb2_setup_geom(pc, wr, bw)) return TB2_ERR_CAPACITY;
+    const int wpl = tb2_wpl_of(pc.chunk);
+    if (wpl > TB2_MAX_WPL || (size_t)nb * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
+    const int bes0 = (half_bw <= mso) ? 0 : mso - half_bw;
+    const int t2 = (int)((double)(half_bw + 1) / epb);
+    const int tmp_len = max(max(half_bw, TB2_MASK_BASES), t2) + 1;
+    const double ls_stop = (double)bes0 + ((double)tmp_len * epb);
+    int first = 0x7fffffff;
+    for (int i = lane; i < tmp_len; i += 32) {
+        const int v = (int)tb2_linspace_at((double)bes0, ls_stop, tmp_len, i);
+        if (i < nb) a.starts[i] = v;
+        if (v >= mso && i < first) first = i;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        first = min(first, __shfl_xor_sync(TB2_FULL_MASK, first, off));
+    __syncwarp();
+    if (first == 0x7fffffff) return TB2_ERR_UNEXPECTED;
+    int mask_seq_len = max(TB2_MASK_BASES, first + 2);
+    if (mask_seq_len > tmp_len) mask_seq_len = tmp_len;
+    if (mask_seq_len > nb) return TB2_ERR_UNEXPECTED;
+    pc.msp_start = (double)(mso + 1);
+    pc.msp_stop = (double)(a.starts[TB2_MASK_BASES - 1] + bw);
+    // validate every masked row (the reference raises from inside the loop)
+    int bad = 0;
+    for (int r = lane; r < mask_seq_len; r += 32) {
+        const int ep = a.starts[r];
+        const int sml = max(mso - ep, 0);
+        int eml = 0;
+        if (r < TB2_MASK_BASES)
+            eml = bw - ((int)tb2_linspace_at(pc.msp_start, pc.msp_stop, TB2_MASK_BASES, r) - ep);
+        if (ep + bw - eml > n_emc) eml = ep + bw - n_emc;
+        const int aa = ep + sml;
+        int bb = ep + bw - eml;
+        if (bb > n_emc) bb = n_emc;
+        const int nv = max(bb - aa, 0);
+        if (aa < 0 || eml < 0 || sml + nv + eml != bw) bad = 1;
+    }
+    if (__any_sync(TB2_FULL_MASK, bad)) return TB2_ERR_MASKED_TOO_FEW;
+    int sel, amax = 0;
+    tb2_init_row0(pc, &sel);
+    st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_MASKED, 0, mask_seq_len, nb, &sel, &amax);
+    if (st != TB2_OK) return st;
+    // ---- adaptive rows :314-412 ----
+    st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_ADAPTIVE, mask_seq_len, nb, nb, &sel, &amax);
+    if (st != TB2_OK) return st;
+    st = tb2_traceback_dyn(wpl, wr.tb, a.starts, nb, pc.W, pc.chunk, amax,
+                           (int)p.band_bound_thresh, a.read_tb);
+    if (st != TB2_OK) return st;
+    // _trim_traceback :754-764
+    if (lane == 0) {
+        int i = 0;
+        while (i <= nb && a.read_tb[i] < 0) a.read_tb[i++] = 0;
+        int e = 1;
+        while (e <= nb + 1 && a.read_tb[nb + 1 - e] > n_emc) { a.read_tb[nb + 1 - e] = n_emc; ++e; }
+    }
+    __syncwarp();
+    return tb2_emit_segs(a, a.cpts + clip, a.n_cpts - clip);
+}

@@ -1,0 +1,44 @@
+// kernels.h -- internal launch interfaces between translation units
+#pragma once
+#include "ctx.h"
+
+// Device-resident batch description for the event->sequence assignment kernel.
+// All arrays live in device memory.  Read r owns
+//   cpts/em        at ev_off[r]   (n_cpts[r] changepoints, n_cpts[r]-1 event means)
+//   rm/rs/starts   at base_off[r] (nb = base_off[r+1]-base_off[r])
+//   read_tb/segs   at base_off[r] + r   (nb + 1 entries)
+struct AlignBatch {
+    int n_reads;
+    const int *cpts;
+    const double *em;
+    const long long *ev_off;
+    const int *n_cpts;        // n_cpts[r * stride]
+    const double *rm, *rs;
+    const long long *base_off;
+    int *starts, *read_tb, *segs;
+    int *rsrtr;        // rsrtr[r * stride]
+    int *status;       // status[r * stride] in/out: processed only where TB2_OK on entry
+    const int *active; // active[r * stride] != 0, may be null (all)
+    int stride;        // element stride (ints) of n_cpts / rsrtr / status / active
+    int *dbg;          // 3 ints per read or null
+    tb2_params params;
+    double sig_match_thresh;
+};
+
+struct AlignLaunchCfg {
+    int smem_cells;       // per-warp row-buffer capacity in shared memory (cells)
+    size_t tb_words;      // per-warp packed-move scratch (uint32 words)
+    int grow_cells;       // per-warp global row scratch capacity (0 = none)
+};
+
+// launches the persistent warp-per-read kernel on ctx->stream
+int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cfg);
+
+// capacity helper (host): packed-move words needed for (rows, W)
+static inline size_t tb2_tb_words(long long rows, long long W)
+{
+    long long chunk = (W + 31) / 32;
+    long long wpl = (chunk + 15) / 16;
+    return (size_t)(rows * wpl * 32);
+}
+static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }

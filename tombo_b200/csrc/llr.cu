@@ -1,0 +1,212 @@
+// llr.cu -- per-read alternative-model log-likelihood ratios:
+// compute_alt_model_read_stats tombo_stats.py:3972-4082 (whole read, '+' strand,
+// single-base motif TomboMotif(alt_base, 1)) with trim_seq_and_means (:3888-3970),
+// c_calc_scaled_llh_ratio_const_var _c_helper.pyx:313-358 (default) and
+// c_calc_llh_ratio_const_var :298-311.  Also c_new_mean_stds :38-57.
+#include "batch.h"
+#include <vector>
+
+namespace {
+enum { L_MEAN = 50, L_MOFF, L_SEQ, L_SOFF, L_START, L_CNT, L_SITEOFF, L_LLR, L_POS, L_A, L_B, L_C, L_D };
+
+struct LlrArgs {
+    int n_reads, K, cpos, alt_code, use_std;
+    double sf, hf, hp;
+    const double *norm_mean;
+    const long long *mean_off, *seq_off, *read_start;
+    const unsigned char *seq;
+    const double *kmeans, *ksds, *alt;   // alt[code * K + pos]
+};
+
+__device__ __forceinline__ int kmer_code(const unsigned char *bases, int K)
+{
+    int c = 0;
+    for (int j = 0; j < K; ++j) c = c * 4 + (bases[j] & 3);
+    return c;
+}
+
+// FILL = false: count sites per read; FILL = true: write llr / pos
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_llr(LlrArgs a, int *counts, const long long *site_off, double *llr_out, long long *pos_out)
+{
+    __shared__ unsigned int warp_tot[8];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const long long mo = a.mean_off[r];
+    const int nb = (int)(a.mean_off[r + 1] - mo);
+    const int K = a.K;
+    // trimmed read sequence: base i = seq[so + cpos + i]
+    const unsigned char *bases = a.seq + a.seq_off[r] + a.cpos;
+    const double *means = a.norm_mean + mo;
+    const int testable = nb - 2 * (K - 1);      // len(motif_search_seq)
+    if (testable <= 0) { if (!FILL && tid == 0) counts[r] = 0; return; }
+    const int per = (testable + 255) / 256;
+    const int i0 = min(testable, tid * per), i1 = min(testable, i0 + per);
+    unsigned int mine = 0;
+    for (int i = i0; i < i1; ++i) mine += (bases[i + K - 1] == a.alt_code);
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned int inc = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    unsigned int base = 0, total = 0;
+    for (int q = 0; q < 8; ++q) { if (q < warp) base += warp_tot[q]; total += warp_tot[q]; }
+    if (!FILL) { if (tid == 0) counts[r] = (int)total; return; }
+    long long o = site_off[r] + base + inc - mine;
+    for (int i = i0; i < i1; ++i) {
+        if (bases[i + K - 1] != a.alt_code) continue;
+        // alt_pos = i: k-mers i .. i+K-1 of the trimmed sequence, means' = means[cpos + .]
+        const double const_var = a.ksds[kmer_code(bases + i, K)];
+        const double cv = const_var * const_var;                 // np.square(r_ref_sds)[alt_pos]
+        double acc = 0.0;
+        for (int t = 0; t < K; ++t) {
+            const int code = kmer_code(bases + i + t, K);
+            const double obs = means[a.cpos + i + t];
+            const double ref_mean = a.kmeans[code];
+            const double alt_mean = a.alt[(size_t)code * K + (K - 1 - t)];
+            if (a.use_std) {
+                const double rd = obs - ref_mean, ad = obs - alt_mean;
+                acc += ((ad * ad) - (rd * rd)) / cv;
+            } else {
+                if (ref_mean == alt_mean) continue;
+                const double scale_mean = (alt_mean + ref_mean) / 2;
+                const double ref_diff = obs - ref_mean, alt_diff = obs - alt_mean;
+                const double scale_diff = obs - scale_mean;
+                double means_diff = alt_mean - ref_mean;
+                if (means_diff < 0) means_diff = means_diff * -1;
+                acc += exp(-(scale_diff * scale_diff) / (a.sf * cv)) *
+                       ((alt_diff * alt_diff) - (ref_diff * ref_diff)) /
+                       (cv * pow(means_diff, a.hp) * a.hf);
+            }
+        }
+        llr_out[o] = acc;
+        pos_out[o] = a.read_start[r] + (K - 1) + i;
+        ++o;
+    }
+}
+
+__global__ void k_mean_stds(const double *sig, const long long *segs, long long n_segs,
+                            double *means, double *sds)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_segs) return;
+    const long long a = segs[i], z = segs[i + 1];
+    double s = 0, v = 0;
+    for (long long k = a; k < z; ++k) s += sig[k];
+    const double m = s / (double)(z - a);
+    means[i] = m;
+    for (long long k = a; k < z; ++k) { const double d = sig[k] - m; v += d * d; }
+    sds[i] = sqrt(v / (double)(z - a));
+}
+}  // namespace
+
+extern "C" int tb2_set_alt_model(tb2_ctx *ctx, const double *alt_means, int kmer_width)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!alt_means || kmer_width < 1 || kmer_width > 12) return TB2_ERR_INVALID_ARG;
+    const size_t n = ((size_t)1 << (2 * kmer_width)) * kmer_width;
+    TB2_CUDA_TRY(ctx, ctx->alt_means.reserve(n * 8));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->alt_means.p, alt_means, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->alt_kmer_width = kmer_width;
+    return TB2_OK;
+}
+
+extern "C" int tb2_alt_model_llr_batch(tb2_ctx *ctx, int64_t n_reads, const double *norm_mean,
+                                       const int64_t *mean_off, const uint8_t *seq,
+                                       const int64_t *seq_off, const int64_t *read_start,
+                                       int alt_base_code, int use_standard_llhr,
+                                       double scale_factor, double height_factor,
+                                       double height_power, double *llr_out, int64_t *pos_out,
+                                       int64_t *site_off)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (n_reads < 0 || !mean_off || !seq_off || !read_start || !site_off || alt_base_code < 0 ||
+        alt_base_code > 3)
+        return TB2_ERR_INVALID_ARG;
+    if (ctx->kmer_width <= 0 || ctx->alt_kmer_width != ctx->kmer_width) {
+        ctx->err = "standard and alternative models must be set with the same k-mer width";
+        return TB2_ERR_INVALID_ARG;
+    }
+    site_off[0] = 0;
+    if (n_reads == 0) return TB2_OK;
+    if (!norm_mean || !seq || !llr_out || !pos_out) return TB2_ERR_INVALID_ARG;
+    const int n = (int)n_reads;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    const size_t tm = (size_t)mean_off[n], ts = (size_t)seq_off[n];
+    TB2_CUDA_TRY(ctx, P[L_MEAN].reserve(tm * 8 + 8));
+    TB2_CUDA_TRY(ctx, P[L_MOFF].reserve((n + 1) * 8));
+    TB2_CUDA_TRY(ctx, P[L_SEQ].reserve(ts + 8));
+    TB2_CUDA_TRY(ctx, P[L_SOFF].reserve((n + 1) * 8));
+    TB2_CUDA_TRY(ctx, P[L_START].reserve((size_t)n * 8));
+    TB2_CUDA_TRY(ctx, P[L_CNT].reserve((size_t)n * 4));
+    TB2_CUDA_TRY(ctx, P[L_SITEOFF].reserve((n + 1) * 8));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_MEAN].p, norm_mean, tm * 8, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_MOFF].p, mean_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_SEQ].p, seq, ts, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_SOFF].p, seq_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_START].p, read_start, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    LlrArgs a;
+    a.n_reads = n; a.K = ctx->kmer_width; a.cpos = ctx->central_pos; a.alt_code = alt_base_code;
+    a.use_std = use_standard_llhr ? 1 : 0;
+    a.sf = scale_factor; a.hf = height_factor; a.hp = height_power;
+    a.norm_mean = P[L_MEAN].as<double>();
+    a.mean_off = P[L_MOFF].as<long long>();
+    a.seq_off = P[L_SOFF].as<long long>();
+    a.read_start = P[L_START].as<long long>();
+    a.seq = P[L_SEQ].as<unsigned char>();
+    a.kmeans = ctx->model_means.as<double>();
+    a.ksds = ctx->model_sds.as<double>();
+    a.alt = ctx->alt_means.as<double>();
+    k_llr<false><<<n, 256, 0, s>>>(a, P[L_CNT].as<int>(), nullptr, nullptr, nullptr);
+    TB2_CHECK_LAUNCH(ctx);
+    std::vector<int> cnt((size_t)n);
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(cnt.data(), P[L_CNT].p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    for (int r = 0; r < n; ++r) site_off[r + 1] = site_off[r] + cnt[r];
+    const size_t total = (size_t)site_off[n];
+    if (total == 0) return TB2_OK;
+    TB2_CUDA_TRY(ctx, P[L_LLR].reserve(total * 8));
+    TB2_CUDA_TRY(ctx, P[L_POS].reserve(total * 8));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_SITEOFF].p, site_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    k_llr<true><<<n, 256, 0, s>>>(a, nullptr, P[L_SITEOFF].as<long long>(), P[L_LLR].as<double>(),
+                                  P[L_POS].as<long long>());
+    TB2_CHECK_LAUNCH(ctx);
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(llr_out, P[L_LLR].p, total * 8, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(pos_out, P[L_POS].p, total * 8, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return TB2_OK;
+}
+
+extern "C" int tb2_new_mean_stds(tb2_ctx *ctx, const double *sig, int64_t n_sig,
+                                 const int64_t *segs, int64_t n_segs, double *means_out,
+                                 double *sds_out)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!sig || !segs || !means_out || !sds_out || n_sig < 1 || n_segs < 1) return TB2_ERR_INVALID_ARG;
+    for (int64_t i = 0; i <= n_segs; ++i)
+        if (segs[i] < 0 || segs[i] > n_sig) return TB2_ERR_INVALID_ARG;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    TB2_CUDA_TRY(ctx, P[L_A].reserve((size_t)n_sig * 8));
+    TB2_CUDA_TRY(ctx, P[L_B].reserve((size_t)(n_segs + 1) * 8));
+    TB2_CUDA_TRY(ctx, P[L_C].reserve((size_t)n_segs * 8));
+    TB2_CUDA_TRY(ctx, P[L_D].reserve((size_t)n_segs * 8));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_A].p, sig, (size_t)n_sig * 8, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_B].p, segs, (size_t)(n_segs + 1) * 8, cudaMemcpyHostToDevice, s));
+    k_mean_stds<<<(unsigned)((n_segs + 127) / 128), 128, 0, s>>>(
+        P[L_A].as<double>(), P[L_B].as<long long>(), n_segs, P[L_C].as<double>(), P[L_D].as<double>());
+    TB2_CHECK_LAUNCH(ctx);
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(means_out, P[L_C].p, (size_t)n_segs * 8, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(sds_out, P[L_D].p, (size_t)n_segs * 8, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return TB2_OK;
+}

@@ -1,0 +1,141 @@
+// select.cuh -- exact order statistics for a 256-thread block (np.median semantics).
+//
+// Radix select on the order-preserving 64-bit image of fp64 values, 8 bits per
+// pass, values produced by a functor (recomputed each pass, nothing is sorted or
+// copied).  np.median = middle order statistic, or (a + b) / 2 of the two middle
+// ones (numpy lib/_function_base_impl.py:_median) -- both are returned exactly.
+#pragma once
+#include "common.cuh"
+
+#define TB2_SEL_THREADS 256
+
+__device__ __forceinline__ unsigned long long tb2_key(double v)
+{
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double tb2_unkey(unsigned long long k)
+{
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+struct SelectSmem {
+    unsigned int hist[256];
+    unsigned int warp_tot[8];
+    unsigned int sel_bin, sel_below, sel_cnt;
+    unsigned long long red_u64[8];
+    unsigned int red_u32[8];
+};
+
+// block-wide sum of an unsigned (all threads get the result)
+__device__ __forceinline__ unsigned int tb2_block_sum(unsigned int v, SelectSmem &sm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(TB2_FULL_MASK, v, off);
+    __syncthreads();
+    if (lane == 0) sm.red_u32[warp] = v;
+    __syncthreads();
+    unsigned int t = 0;
+#pragma unroll
+    for (int w = 0; w < TB2_SEL_THREADS / 32; ++w) t += sm.red_u32[w];
+    return t;
+}
+
+__device__ __forceinline__ unsigned long long tb2_block_min_u64(unsigned long long v,
+                                                                SelectSmem &sm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(TB2_FULL_MASK, v, off);
+        v = o < v ? o : v;
+    }
+    __syncthreads();
+    if (lane == 0) sm.red_u64[warp] = v;
+    __syncthreads();
+    unsigned long long t = sm.red_u64[0];
+#pragma unroll
+    for (int w = 1; w < TB2_SEL_THREADS / 32; ++w) t = sm.red_u64[w] < t ? sm.red_u64[w] : t;
+    return t;
+}
+
+// Key of the element of ascending rank k (0-based) among the n values f(i) with
+// pred(i) true.  Requires 0 <= k < count(pred).  All 256 threads participate.
+template <class F, class Pred>
+__device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k, SelectSmem &sm)
+{
+    unsigned long long prefix = 0, mask = 0;
+    unsigned int kk = (unsigned int)k;
+    const int tid = threadIdx.x;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        sm.hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += TB2_SEL_THREADS) {
+            if (!pred(i)) continue;
+            const unsigned long long key = tb2_key(f(i));
+            if ((key & mask) == prefix) atomicAdd(&sm.hist[(unsigned int)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        // inclusive scan of the 256 bins (thread t <-> bin t)
+        const unsigned int h = sm.hist[tid];
+        unsigned int inc = h;
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int o = __shfl_up_sync(TB2_FULL_MASK, inc, off);
+            if (lane >= off) inc += o;
+        }
+        if (lane == 31) sm.warp_tot[warp] = inc;
+        __syncthreads();
+        unsigned int base = 0;
+        for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+        inc += base;
+        const unsigned int exc = inc - h;
+        if (h > 0 && exc <= kk && kk < inc) { sm.sel_bin = tid; sm.sel_below = exc; sm.sel_cnt = h; }
+        __syncthreads();
+        prefix |= (unsigned long long)sm.sel_bin << shift;
+        mask |= 0xffULL << shift;
+        kk -= sm.sel_below;
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// values of rank k and k+1 (k+1 only if want2); exact
+template <class F, class Pred>
+__device__ void tb2_block_select2(F f, Pred pred, int n, int k, bool want2, double *v0,
+                                  double *v1, SelectSmem &sm)
+{
+    const unsigned long long K = tb2_block_select_key(f, pred, n, k, sm);
+    *v0 = tb2_unkey(K);
+    *v1 = *v0;
+    if (!want2) return;
+    unsigned int cnt_le = 0;
+    unsigned long long min_gt = ~0ULL;
+    for (int i = threadIdx.x; i < n; i += TB2_SEL_THREADS) {
+        if (!pred(i)) continue;
+        const unsigned long long key = tb2_key(f(i));
+        if (key <= K) ++cnt_le;
+        else if (key < min_gt) min_gt = key;
+    }
+    cnt_le = tb2_block_sum(cnt_le, sm);
+    min_gt = tb2_block_min_u64(min_gt, sm);
+    if (cnt_le <= (unsigned int)(k + 1)) *v1 = tb2_unkey(min_gt);
+}
+
+struct PredAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
+
+// np.median of f(0..n-1)
+template <class F>
+__device__ double tb2_block_median(F f, int n, SelectSmem &sm)
+{
+    double a, b;
+    if (n & 1) {
+        tb2_block_select2(f, PredAll(), n, n / 2, false, &a, &b, sm);
+        return a;
+    }
+    tb2_block_select2(f, PredAll(), n, n / 2 - 1, true, &a, &b, sm);
+    return (a + b) / 2.0;
+}

@@ -1,0 +1,1033 @@
+// stage_kernels.cu -- the non-DP stages of resquiggle_read as batched kernels
+// (sm_100a): signal conversion + k-mer lookup, normalisation, changepoint
+// detection, event means, skipped-base raw-signal DP, base means, Theil-Sen
+// rescaling, final scoring.  One CTA (or warp) per read; arithmetic follows the
+// reference operation for operation (see DESIGN.md "Arithmetic contract").
+#include "batch.h"
+#include "select.cuh"
+
+#define ST_THREADS TB2_SEL_THREADS
+
+__device__ __forceinline__ bool rd_active(const ReadState &s) { return s.active && s.status == TB2_OK; }
+
+// ===========================================================================
+// prep: raw -> fp64 (reversed for RNA), k-mer level lookup, state init
+// TomboModel.get_exp_levels_from_seq tombo_stats.py:834-862; RNA flip
+// resquiggle.py:1516
+// ===========================================================================
+template <class T>
+__global__ void __launch_bounds__(ST_THREADS)
+k_prep(BatchView b, const T *raw, int is_rna, const double *kmeans, const double *ksds)
+{
+    const int r = blockIdx.x;
+    const long long ro = b.raw_off[r];
+    const int n = (int)(b.raw_off[r + 1] - ro);
+    for (int i = threadIdx.x; i < n; i += ST_THREADS)
+        b.rawf[ro + i] = (double)raw[ro + (is_rna ? n - 1 - i : i)];
+    const long long so = b.seq_off[r], bo = b.base_off[r];
+    const int nb = (int)(b.base_off[r + 1] - bo);
+    const int K = b.kmer_width;
+    int bad = 0;
+    for (int i = threadIdx.x; i < nb; i += ST_THREADS) {
+        int code = 0;
+        for (int j = 0; j < K; ++j) {
+            const int c = b.seq[so + i + j];
+            if (c > 3) bad = 1;
+            code = code * 4 + (c & 3);
+        }
+        b.rm[bo + i] = kmeans[code];
+        b.rs[bo + i] = ksds[code];
+    }
+    const int any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        ReadState s;
+        memset(&s, 0, sizeof(s));
+        s.status = TB2_OK;
+        if (n <= 0) s.status = TB2_ERR_NO_RAW;
+        if (nb <= 0 || (int)(b.seq_off[r + 1] - so) != nb + K - 1) s.status = TB2_ERR_DISCORDANT_LEN;
+        if (any_bad) s.status = TB2_ERR_INVALID_SEQ;
+        s.done = (s.status != TB2_OK);
+        b.st[r] = s;
+    }
+}
+
+// worker policy bookkeeping (resquiggle.py:1492-1504, 1578-1588)
+__global__ void k_start_attempt(BatchView b, int attempt)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= b.n_reads) return;
+    ReadState &s = b.st[r];
+    if (s.done) { s.active = 0; return; }
+    if (attempt == 0) {
+        s.active = 1;
+    } else {
+        if (s.status == TB2_OK) { s.active = 0; s.done = 1; return; }  // defensive
+        s.first_status = s.status;
+        s.status = TB2_OK;
+        s.active = 1;
+    }
+    s.attempt = attempt;
+    s.n_iters = 0;
+    s.use_sv = 0;
+}
+
+// compute_num_events (tombo_stats.py:1558-1574) + the signal/sequence guard of
+// resquiggle_read (resquiggle.py:1154-1160)
+__global__ void k_begin_call(BatchView b, tb2_params p, StagePolicy pol)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= b.n_reads) return;
+    ReadState &s = b.st[r];
+    if (!rd_active(s)) return;
+    const int n = (int)(b.raw_off[r + 1] - b.raw_off[r]);
+    const int nb = (int)(b.base_off[r + 1] - b.base_off[r]);
+    const long long a = (long long)n / p.mean_obs_per_event;
+    const long long c = (long long)((double)nb * pol.min_event_to_seq_ratio);
+    const long long ne = a > c ? a : c;
+    if ((double)ne / (double)p.bandwidth > (double)nb) { s.status = TB2_ERR_TOO_MUCH_SIGNAL; return; }
+    if (ne > b.ev_off[r + 1] - b.ev_off[r] || ne < 2) { s.status = TB2_ERR_CAPACITY; return; }
+    s.num_events = (int)ne;
+}
+
+__global__ void k_end_call(BatchView b, int max_iters)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= b.n_reads) return;
+    ReadState &s = b.st[r];
+    if (!s.active) return;
+    s.calls += 1;
+    if (s.status != TB2_OK) { s.active = 0; return; }  // attempt failed
+    s.n_iters += 1;
+    if (s.changed && s.n_iters < max_iters) { s.use_sv = 1; return; }  // iterate
+    s.active = 0;
+    s.done = 1;
+}
+
+__global__ void k_count_active(BatchView b, int *counters)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int act = 0, fail = 0;
+    if (r < b.n_reads) {
+        act = b.st[r].active != 0;
+        fail = (!b.st[r].done && b.st[r].status != TB2_OK);
+    }
+    act = __syncthreads_count(act);
+    fail = __syncthreads_count(fail);
+    if (threadIdx.x == 0) {
+        if (act) atomicAdd(&counters[0], act);
+        if (fail) atomicAdd(&counters[1], fail);
+    }
+}
+
+// ===========================================================================
+// normalize_raw_signal tombo_stats.py:482-573 (+ c_apply_outlier_thresh
+// _c_helper.pyx:73-87)
+// ===========================================================================
+__global__ void __launch_bounds__(ST_THREADS)
+k_normalize(BatchView b, StagePolicy pol, int first_call)
+{
+    __shared__ SelectSmem sm;
+    const int r = blockIdx.x;
+    ReadState &s = b.st[r];
+    if (!rd_active(s)) return;
+    const long long ro = b.raw_off[r];
+    const int n = (int)(b.raw_off[r + 1] - ro);
+    const double *raw = b.rawf + ro;
+    double *norm = b.norm + ro;
+    double shift, scale, lo = NAN, hi = NAN;
+    const bool given = s.use_sv != 0;
+    const bool use_const = first_call && !isnan(pol.const_scale);
+    if (!given) {
+        shift = tb2_block_median([&](int i) { return raw[i]; }, n, sm);              // :541/:545
+        if (use_const) scale = pol.const_scale;                                       // :546
+        else scale = tb2_block_median([&](int i) { return fabs(raw[i] - shift); }, n, sm);  // :542
+    } else {
+        shift = s.sv.shift; scale = s.sv.scale;
+    }
+    if (scale == 0.0 || isnan(scale)) {  // FloatingPointError under np.seterr(all='raise')
+        if (threadIdx.x == 0) s.status = TB2_ERR_UNEXPECTED;
+        return;
+    }
+    for (int i = threadIdx.x; i < n; i += ST_THREADS) norm[i] = (raw[i] - shift) / scale;  // :554
+    __syncthreads();
+    const double thresh = given ? NAN : pol.outlier_thresh;
+    if (!isnan(thresh)) {                                                             // :559-563
+        const double med = tb2_block_median([&](int i) { return norm[i]; }, n, sm);
+        const double mad = tb2_block_median([&](int i) { return fabs(norm[i] - med); }, n, sm);
+        lo = med - (mad * thresh);
+        hi = med + (mad * thresh);
+    } else if (given) { lo = s.sv.lower_lim; hi = s.sv.upper_lim; }                   // :565-566
+    if (!isnan(lo) && !isnan(hi)) {
+        for (int i = threadIdx.x; i < n; i += ST_THREADS) {
+            const double v = norm[i];
+            norm[i] = v > hi ? hi : (v < lo ? lo : v);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s.sv.shift = shift; s.sv.scale = scale; s.sv.lower_lim = lo; s.sv.upper_lim = hi;
+        s.sv.outlier_thresh = thresh;
+    }
+}
+
+// ===========================================================================
+// changepoints: c_valid_cpts_w_cap / c_valid_cpts_w_cap_t_test
+// (_c_helper.pyx:89-120 / 144-202) + sort (tombo_helper.py:76-91)
+// + remove_stall_cpts (tombo_stats.py:1576-1597)
+//
+// The reference ranks all candidates (argsort, descending) and picks greedily
+// with a +-(min_base_obs-1) exclusion zone until num_cpts are found.  Here the
+// same set is obtained without a sort: a candidate is accepted iff every
+// higher-ranked candidate inside its zone is rejected (iterated to the fixed
+// point, which is the greedy result), then the num_cpts best accepted ones are
+// kept via an exact radix select.  Rank order: score descending, ties -> larger
+// position first (the pinned rule of SURVEY.md 8c-7).
+// ===========================================================================
+__device__ __forceinline__ bool cand_gt(double si, int i, double sk, int k)
+{
+    return si > sk || (si == sk && i > k);
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+k_cpts(BatchView b, tb2_params p, int on_raw)
+{
+    __shared__ SelectSmem sm;
+    __shared__ int s_flag;
+    const int r = blockIdx.x;
+    ReadState &s = b.st[r];
+    if (!rd_active(s)) return;
+    const int tid = threadIdx.x;
+    const long long ro = b.raw_off[r];
+    const int n = (int)(b.raw_off[r + 1] - ro);
+    const double *sig = (on_raw ? b.rawf : b.norm) + ro;
+    double *cs = b.cs + ro + r;
+    double *sc = b.scores + ro;
+    volatile unsigned char *state = b.cstate + ro;
+    const int w = (int)p.running_stat_width, m = (int)p.min_obs_per_base;
+    const int N = s.num_events;
+    int n_cand, bound;
+    if (!p.use_t_test_seg) {
+        n_cand = n + 1 - 2 * w;
+        bound = n_cand - 2 * w;  // num_cands = candidate_poss.shape[0] - 2*w (:105-106)
+        if (n_cand <= 0) { if (tid == 0) s.status = TB2_ERR_UNEXPECTED; return; }
+        // np.cumsum(concatenate([[0.0], signal])): strictly sequential fp64 sums.
+        // One warp; every lane carries the running sum through 32 shuffled adds.
+        if (tid < 32) {
+            double acc = 0.0;
+            if (tid == 0) cs[0] = 0.0;
+            for (int base = 0; base < n; base += 32) {
+                const double x = (base + tid < n) ? sig[base + tid] : 0.0;
+                double mine = 0.0;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    acc = acc + __shfl_sync(TB2_FULL_MASK, x, k);
+                    if (tid == k) mine = acc;
+                }
+                if (base + tid < n) cs[base + tid + 1] = mine;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < n_cand; i += ST_THREADS) {
+            sc[i] = fabs(((2 * cs[i + w]) - cs[i]) - cs[i + 2 * w]);   // :95-98
+            state[i] = 0;
+        }
+    } else {
+        n_cand = n - 2 * w;
+        bound = n_cand;      // :199
+        if (n_cand <= 0) { if (tid == 0) s.status = TB2_ERR_UNEXPECTED; return; }
+        for (int pos = tid; pos < n_cand; pos += ST_THREADS) {           // :153-179
+            double m1 = 0, m2 = 0, var1 = 0, var2 = 0, d;
+            for (int k = 0; k < w; ++k) m1 += sig[pos + k];
+            m1 /= (double)w;
+            for (int k = 0; k < w; ++k) m2 += sig[pos + w + k];
+            m2 /= (double)w;
+            for (int k = 0; k < w; ++k) { d = sig[pos + k] - m1; var1 += d * d; }
+            for (int k = 0; k < w; ++k) { d = sig[pos + w + k] - m2; var2 += d * d; }
+            double t;
+            if (var1 + var2 == 0) t = 0.0;
+            else if (m1 > m2) t = (m1 - m2) / sqrt(var1 + var2);
+            else t = (m2 - m1) / sqrt(var1 + var2);
+            sc[pos] = t;
+            state[pos] = 0;
+        }
+    }
+    if (N < 1 || N > n_cand) { if (tid == 0) s.status = (N < 1) ? TB2_ERR_UNEXPECTED : TB2_ERR_FEWER_CPTS; return; }
+    __syncthreads();
+    // ---- greedy exclusion as a fixed point ----
+    for (;;) {
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        int undecided = 0;
+        for (int i = tid; i < n_cand; i += ST_THREADS) {
+            if (state[i] != 0) continue;
+            const double si = sc[i];
+            bool acc_nb = false, blocked = false;
+            const int k0 = max(0, i - m + 1), k1 = min(n_cand - 1, i + m - 1);
+            for (int k = k0; k <= k1; ++k) {
+                if (k == i) continue;
+                const unsigned char stt = state[k];
+                if (stt == 1) acc_nb = true;
+                else if (stt == 0 && cand_gt(sc[k], k, si, i)) blocked = true;
+            }
+            if (acc_nb) state[i] = 2;
+            else if (!blocked) state[i] = 1;
+            else undecided = 1;
+        }
+        if (undecided) s_flag = 1;
+        __syncthreads();
+        const int again = s_flag;
+        __syncthreads();
+        if (!again) break;
+    }
+    // ---- keep the N best accepted ----
+    unsigned int acc_cnt = 0;
+    for (int i = tid; i < n_cand; i += ST_THREADS) acc_cnt += (state[i] == 1);
+    acc_cnt = tb2_block_sum(acc_cnt, sm);
+    if ((int)acc_cnt < N) { if (tid == 0) s.status = TB2_ERR_FEWER_CPTS; return; }
+    double vN, dummy;
+    auto f_score = [&](int i) { return sc[i]; };
+    auto p_acc = [&](int i) { return state[i] == 1; };
+    tb2_block_select2(f_score, p_acc, n_cand, (int)acc_cnt - N, false, &vN, &dummy, sm);
+    unsigned int g = 0, e = 0;
+    for (int i = tid; i < n_cand; i += ST_THREADS) {
+        if (state[i] != 1) continue;
+        g += sc[i] > vN;
+        e += sc[i] == vN;
+    }
+    g = tb2_block_sum(g, sm);
+    e = tb2_block_sum(e, sm);
+    const int need = N - (int)g;   // 1 <= need <= e, taken from the largest positions
+    int posN;
+    {
+        auto f_pos = [&](int i) { return (double)i; };
+        auto p_tie = [&](int i) { return state[i] == 1 && sc[i] == vN; };
+        double pv, pd;
+        tb2_block_select2(f_pos, p_tie, n_cand, (int)e - need, false, &pv, &pd, sm);
+        posN = (int)pv;
+    }
+    // rank index of the N-th pick in the full candidate order (:109-118)
+    unsigned int higher = 0;
+    for (int i = tid; i < n_cand; i += ST_THREADS)
+        higher += (sc[i] > vN) || (sc[i] == vN && i > posN);
+    higher = tb2_block_sum(higher, sm);
+    if (N > 1 && (int)higher + 1 >= bound) { if (tid == 0) s.status = TB2_ERR_FEWER_CPTS; return; }
+    // ---- ordered compaction (+ w), dropping changepoints inside stalls ----
+    const int per = (n_cand + ST_THREADS - 1) / ST_THREADS;
+    const int i0 = min(n_cand, tid * per), i1 = min(n_cand, i0 + per);
+    const int *si = b.stall_ints ? b.stall_ints + 2 * (size_t)b.stall_cap * r : nullptr;
+    const int ns = b.stall_ints ? s.n_stalls : 0;
+    auto keep = [&](int i) {
+        if (state[i] != 1) return false;
+        if (!(sc[i] > vN || (sc[i] == vN && i >= posN))) return false;
+        const int c = i + w;
+        for (int k = 0; k < ns; ++k) if (si[2 * k] < c && c < si[2 * k + 1]) return false;
+        return true;
+    };
+    unsigned int mine = 0;
+    for (int i = i0; i < i1; ++i) mine += keep(i);
+    // exclusive scan over threads
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned int inc = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int o = __shfl_up_sync(TB2_FULL_MASK, inc, off);
+        if (lane >= off) inc += o;
+    }
+    __syncthreads();
+    if (lane == 31) sm.warp_tot[warp] = inc;
+    __syncthreads();
+    unsigned int base = 0, total = 0;
+    for (int q = 0; q < ST_THREADS / 32; ++q) { if (q < warp) base += sm.warp_tot[q]; total += sm.warp_tot[q]; }
+    unsigned int o = base + inc - mine;
+    int *cp = b.cpts + b.ev_off[r];
+    for (int i = i0; i < i1; ++i) if (keep(i)) cp[o++] = i + w;
+    if (tid == 0) {
+        s.n_cpts = (int)total;
+        if (total < 2) s.status = TB2_ERR_UNEXPECTED;
+    }
+}
+
+// ===========================================================================
+// c_new_means _c_helper.pyx:59-71 over the changepoints (event means)
+// ===========================================================================
+__global__ void __launch_bounds__(ST_THREADS) k_event_means(BatchView b)
+{
+    const int r = blockIdx.x;
+    const ReadState &s = b.st[r];
+    if (!rd_active(s)) return;
+    const double *norm = b.norm + b.raw_off[r];
+    const int *cp = b.cpts + b.ev_off[r];
+    double *em = b.em + b.ev_off[r];
+    const int ne = s.n_cpts - 1;
+    for (int e = threadIdx.x; e < ne; e += ST_THREADS) {
+        const int a = cp[e], z = cp[e + 1];
+        double acc = 0;
+        for (int k = a; k < z; ++k) acc += norm[k];
+        em[e] = acc / (double)(z - a);
+    }
+}
+
+// get_scale_values_from_events tombo_stats.py:217-233 (RNA, first call)
+__global__ void __launch_bounds__(ST_THREADS) k_rna_scale(BatchView b, StagePolicy pol)
+{
+    __shared__ SelectSmem sm;
+    const int r = blockIdx.x;
+    ReadState &s = b.st[r];
+    if (!rd_active(s) || s.use_sv == 1) return;
+    const double *raw = b.rawf + b.raw_off[r];
+    const int *cp = b.cpts + b.ev_off[r];
+    double *em = b.em + b.ev_off[r];
+    int ne = 10000;                                         // RNA_SCALE_NUM_EVENTS
+    if ((double)s.n_cpts * 0.75 < (double)ne) ne = (int)((double)s.n_cpts * 0.75);
+    if (ne < 2) { if (threadIdx.x == 0) s.status = TB2_ERR_UNEXPECTED; return; }
+    for (int e = threadIdx.x; e < ne - 1; e += ST_THREADS) {
+        const int a = cp[e], z = cp[e + 1];
+        double acc = 0;
+        for (int k = a; k < z; ++k) acc += raw[k];
+        em[e] = acc / (double)(z - a);
+    }
+    __syncthreads();
+    const double med = tb2_block_median([&](int i) { return em[i]; }, ne - 1, sm);
+    const double mad = tb2_block_median([&](int i) { return fabs(em[i] - med); }, ne - 1, sm);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s.sv.shift = med; s.sv.scale = mad;
+        s.sv.lower_lim = -pol.outlier_thresh; s.sv.upper_lim = pol.outlier_thresh;
+        s.sv.outlier_thresh = NAN;
+        s.use_sv = 2;   // consumed by k_normalize of this call
+    }
+}
+
+// ===========================================================================
+// identify_stalls (mean-window method) tombo_stats.py:269-368,
+// MEAN_STALL_PARAMS _default_parameters.py:93-97.  Once per read (RNA).
+// ===========================================================================
+__global__ void __launch_bounds__(ST_THREADS) k_stalls(BatchView b)
+{
+    const int r = blockIdx.x;
+    ReadState &s = b.st[r];
+    if (s.done) return;
+    const int tid = threadIdx.x;
+    const long long ro = b.raw_off[r];
+    const int n = (int)(b.raw_off[r + 1] - ro);
+    const double *raw = b.rawf + ro;
+    double *cs = b.cs + ro + r;        // cumsum, then moving averages
+    double *metric = b.scores + ro;    // diff sums
+    volatile unsigned char *below = b.cstate + ro;
+    const int window = 350, mini = 50, nwin = 7, min_consec = 200, edge = 100;
+    const double thresh = 40;
+    if (tid == 0) s.n_stalls = 0;
+    if (n < window) return;
+    if (tid < 32) {   // np.cumsum(all_raw_signal): sequential
+        double acc = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const double x = (base + tid < n) ? raw[base + tid] : 0.0;
+            double mine = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                acc = (base + k == 0) ? __shfl_sync(TB2_FULL_MASK, x, k)
+                                      : acc + __shfl_sync(TB2_FULL_MASK, x, k);
+                if (tid == k) mine = acc;
+            }
+            if (base + tid < n) cs[base + tid] = mine;
+        }
+    }
+    __syncthreads();
+    const int n_ma = n - (mini - 1);
+    const int n_off = n_ma - mini * (nwin - 1);
+    // mav[k] = (cs[k+49] - cs[k-1]) / 50 ; first window: cs[49] / 50   (:277-282)
+    auto mav = [&](int k) {
+        const int i = k + mini - 1;
+        const double v = (i >= mini) ? cs[i] - cs[i - mini] : cs[i];
+        return v / (double)mini;
+    };
+    for (int q = tid; q < n_off; q += ST_THREADS) {
+        double off[7];
+#pragma unroll
+        for (int o = 0; o < 7; ++o) off[o] = mav(q + mini * o);
+        double sum = fabs(off[0] - off[1]);                  // diffs[0].copy() (:298)
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+#pragma unroll
+            for (int j = i + 1; j < 7; ++j) sum += fabs(off[i] - off[j]);
+        metric[q] = sum / 21.0;
+    }
+    const int start_off = (int)((double)window * 0.5);
+    for (int i = tid; i < n; i += ST_THREADS) below[i] = 0;
+    __syncthreads();
+    for (int q = tid; q < n_off; q += ST_THREADS) below[start_off + q] = metric[q] <= thresh;
+    __syncthreads();
+    if (tid == 0) {
+        int *out = b.stall_ints + 2 * (size_t)b.stall_cap * r;
+        const int expand = window / 2 - edge;
+        int no = 0, have = 0, ps = 0, pe = 0, i = 0, overflow = 0;
+        while (i < n) {
+            if (below[i]) {
+                int j = i;
+                while (j < n && below[j]) ++j;
+                if (j - i > min_consec) {
+                    const int a = i - expand, z = j + expand;
+                    if (!have) { ps = a; pe = z; have = 1; }
+                    else if (a > pe) {
+                        if (no < b.stall_cap) { out[2 * no] = ps; out[2 * no + 1] = pe; } else overflow = 1;
+                        ++no; ps = a; pe = z;
+                    } else pe = z;
+                }
+                i = j;
+            } else ++i;
+        }
+        if (have) {
+            if (no < b.stall_cap) { out[2 * no] = ps; out[2 * no + 1] = pe; } else overflow = 1;
+            ++no;
+        }
+        s.n_stalls = no;
+        if (overflow) { s.status = TB2_ERR_CAPACITY; s.done = 1; }
+    }
+}
+
+// ===========================================================================
+// resolve_skipped_bases_with_raw resquiggle.py:402-540 with c_reg_z_scores,
+// c_base_forward_pass, c_base_traceback (_c_dynamic_programming.pyx:34-182).
+// Small serial DPs: one warp per read, lane 0 walks the windows.
+// ===========================================================================
+struct RawCtx {
+    const double *sig;   // window signal (norm + rsrtr + sig_start)
+    const double *rm, *rs;
+    int n_ev, L, m;
+    int winsor;
+    double mhz;
+    double *fwd;         // n_ev x L
+    double *cs;          // L
+    int *ld0, *ld1;      // L each
+};
+
+__device__ __forceinline__ double raw_z(const RawCtx &c, int row, int i)
+{
+    // c_base_z_scores :17-32 on r_sig[b_start + i]
+    double z = (c.sig[row * c.m + i] - c.rm[row]) / c.rs[row];
+    if (z > 0) z = -z;
+    if (c.winsor && z < -c.mhz) z = -c.mhz;
+    return z;
+}
+
+__device__ int raw_window(RawCtx &c, int *new_segs)
+{
+    const int L = c.L, m = c.m, n_ev = c.n_ev;
+    if (n_ev < 2 || L < 1) return TB2_ERR_UNEXPECTED;
+    // raw_forward_pass resquiggle.py:345-380 -- first row is a cumsum
+    {
+        double acc = 0;
+        for (int i = 0; i < L; ++i) { acc = (i == 0) ? raw_z(c, 0, 0) : acc + raw_z(c, 0, i); c.fwd[i] = acc; c.ld0[i] = m; }
+    }
+    int *pld = c.ld0, *cld = c.ld1;
+    for (int r = 1; r < n_ev; ++r) {
+        const double *pf = c.fwd + (size_t)(r - 1) * L;
+        double *bf = c.fwd + (size_t)r * L;
+        // c_base_forward_pass :99-163; rows: start r*m, end r*m + L
+        const int b_start = r * m, p_start = (r - 1) * m, p_end = p_start + L, b_end = b_start + L;
+        if (m > 1) {
+            double acc = 0;
+            for (int i = 0; i < L; ++i) { acc = (i == 0) ? raw_z(c, r - 1, 0) : acc + raw_z(c, r - 1, i); c.cs[i] = acc; }
+        }
+        if (b_start - p_start - 1 < 0 || b_start - p_start - 1 >= L) return TB2_ERR_UNEXPECTED;
+        bf[0] = raw_z(c, r, 0) + pf[b_start - p_start - 1];
+        cld[0] = 1;
+        for (int pos = b_start + 1; pos < p_end + 1; ++pos) {
+            int lag = 1;
+            for (;;) {
+                const int ix = pos - p_start - lag;
+                if (ix < 0 || ix >= L) return TB2_ERR_UNEXPECTED;
+                if (pld[ix] + lag <= m) ++lag; else break;
+            }
+            double diag = pf[pos - p_start - lag];
+            if (lag > 1) {
+                if (pos - p_start - 1 >= L) return TB2_ERR_UNEXPECTED;
+                diag += c.cs[pos - p_start - 1] - c.cs[pos - p_start - lag];
+            }
+            if (pos - b_start >= L) return TB2_ERR_UNEXPECTED;
+            const double stay = bf[pos - b_start - 1];
+            double score; int dv;
+            if (diag > stay) { score = diag; dv = 1; }
+            else { score = stay; dv = cld[pos - b_start - 1] + 1; }
+            bf[pos - b_start] = raw_z(c, r, pos - b_start) + score;
+            cld[pos - b_start] = dv;
+        }
+        if (b_end > p_end + 1) {
+            double fv = bf[p_end - b_start];
+            int cl = cld[p_end - b_start];
+            const int left = b_end - p_end - 1;
+            for (int i = 0; i < left; ++i) {
+                fv += raw_z(c, r, i + p_end - b_start + 1);
+                cl += 1;
+                bf[i + p_end - b_start + 1] = fv;
+                cld[i + p_end - b_start + 1] = cl;
+            }
+        }
+        int *t = pld; pld = cld; cld = t;
+    }
+    // raw_traceback resquiggle.py:382-400 with c_base_traceback :165-182
+    int sig_start = (n_ev - 1) * m + L - 1;   // curr_end - 1
+    for (int bp = n_ev - 2; bp >= 0; --bp) {
+        const int cur = bp + 1;
+        const double *cf = c.fwd + (size_t)cur * L, *nf = c.fwd + (size_t)bp * L;
+        const int c_start = cur * m, n_start = bp * m, n_end = n_start + L;
+        int cbs = 1, found = -1;
+        for (int sp = sig_start; sp >= 0; --sp) {
+            cbs += 1;
+            if (cbs <= m || sp - 1 >= n_end) continue;
+            if (sp <= c_start) { found = sp; break; }
+            const int a = sp - n_start - 1, q = sp - c_start - 1;
+            if (a < 0 || a >= L || q < 0 || q >= L) return TB2_ERR_UNEXPECTED;
+            if (nf[a] > cf[q]) { found = sp; break; }
+        }
+        if (found < 0) return TB2_ERR_UNEXPECTED;   // reference: None -> TypeError
+        new_segs[bp] = found;
+        sig_start = found - 1;
+    }
+    return TB2_OK;
+}
+
+#define DEL_FIX_WINDOW 2
+#define MAX_DEL_FIX_WINDOW 10
+#define EXTRA_SIG_FACTOR 1.1
+
+__global__ void __launch_bounds__(128)
+k_resolve(BatchView b, tb2_params p, StagePolicy pol, double *pool, size_t cap, int *counter)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    double *scr = pool + slot * cap;
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(counter, 1);
+        r = __shfl_sync(TB2_FULL_MASK, r, 0);
+        if (r >= b.n_reads) break;
+        ReadState &s = b.st[r];
+        if (!rd_active(s)) continue;
+        const long long bo = b.base_off[r];
+        const int nb = (int)(b.base_off[r + 1] - bo);
+        const int *segs = b.segs_dp + bo + r;
+        int *out = b.segs + bo + r;
+        for (int i = lane; i <= nb; i += 32) out[i] = segs[i];
+        __syncwarp();
+        if (lane != 0) continue;
+        const int n_norm = segs[nb];
+        s.n_norm = n_norm;
+        const double *norm = b.norm + b.raw_off[r] + s.rsrtr;
+        const double *rm = b.rm + bo, *rs = b.rs + bo;
+        int *ws = b.starts + bo, *we = b.read_tb + bo + r;   // scratch (>= nb entries each)
+        const int n_segs = nb + 1;
+        const int m = (int)p.raw_min_obs_per_base;
+        int nw = 0, st = TB2_OK;
+        for (int d = 0; d < nb; ++d) {                                   // :465-472
+            if (segs[d + 1] - segs[d] != 0) continue;
+            if (nw > 0 && d < we[nw - 1] + DEL_FIX_WINDOW) we[nw - 1] = d + DEL_FIX_WINDOW + 1;
+            else { ws[nw] = d - DEL_FIX_WINDOW; we[nw] = d + DEL_FIX_WINDOW + 1; ++nw; }
+        }
+        if (nw == 0) continue;
+#define TOO_SMALL(a, z) ((double)(segs[z] - segs[a]) <= ((double)(((z) - (a) + 1) * m)) * EXTRA_SIG_FACTOR)
+#define MERGE_TRIM() do { \
+            int mm = 0; \
+            for (int k = 0; k < nw; ++k) { \
+                if (mm > 0 && ws[k] < we[mm - 1]) we[mm - 1] = we[k]; \
+                else { ws[mm] = ws[k]; we[mm] = we[k]; ++mm; } } \
+            nw = mm; \
+            if (ws[0] < 0) ws[0] = 0; \
+            if (we[nw - 1] > n_segs - 1) we[nw - 1] = n_segs - 1; } while (0)
+        MERGE_TRIM();
+        int expanded = 0;
+        for (int it = 0; it < MAX_DEL_FIX_WINDOW - DEL_FIX_WINDOW; ++it) {   // :481-486
+            expanded = 0;
+            for (int k = 0; k < nw; ++k)
+                if (TOO_SMALL(ws[k], we[k])) { expanded = 1; ws[k] -= 1; we[k] += 1; }
+            if (!expanded) break;
+            MERGE_TRIM();
+        }
+        if (expanded)
+            for (int k = 0; k < nw; ++k)
+                if (TOO_SMALL(ws[k], we[k])) { st = TB2_ERR_NOT_ENOUGH_DEL_SIGNAL; break; }
+        if (st == TB2_OK && pol.max_raw_cpts >= 0) {
+            int mx = 0;
+            for (int k = 0; k < nw; ++k) mx = max(mx, we[k] - ws[k]);
+            if (mx > pol.max_raw_cpts) st = TB2_ERR_TOO_MANY_DELS;
+        }
+        for (int k = 0; k < nw && st == TB2_OK; ++k) {                    // :506-531
+            const int a = ws[k], z = we[k], n_ev = z - a;
+            const int sig_start = segs[a], sig_len = segs[z] - segs[a];
+            if (sig_start < 0 || sig_start + sig_len > n_norm) { st = TB2_ERR_UNEXPECTED; break; }
+            RawCtx c;
+            c.sig = norm + sig_start; c.rm = rm + a; c.rs = rs + a;
+            c.n_ev = n_ev; c.m = m;
+            // c_reg_z_scores with max_base_shift = n_events: starts idx*m, ends
+            // sig_len - (n_ev-1-idx)*m  (:56-81)  => every row has the same length
+            c.L = sig_len - (n_ev - 1) * m;
+            c.winsor = !isnan(p.max_half_z_score);
+            c.mhz = c.winsor ? p.max_half_z_score : 0.0;
+            if (c.L < 1) { st = TB2_ERR_UNEXPECTED; break; }
+            const size_t need = (size_t)n_ev * c.L + 2 * (size_t)c.L + 8;
+            if (need > cap) { st = TB2_ERR_CAPACITY; break; }
+            c.fwd = scr;
+            c.cs = scr + (size_t)n_ev * c.L;
+            c.ld0 = (int *)(c.cs + c.L);
+            c.ld1 = c.ld0 + c.L;
+            // new segs land in out[a+1 .. z-1]
+            st = raw_window(c, out + a + 1);
+            if (st == TB2_OK) for (int i = 0; i < n_ev - 1; ++i) out[a + 1 + i] += sig_start;
+        }
+        if (st == TB2_OK) {
+            for (int i = 0; i < nb; ++i) if (out[i + 1] - out[i] < 1) { st = TB2_ERR_ZERO_LEN_SEG; break; }
+            if (st == TB2_OK && out[0] < 0) st = TB2_ERR_NEG_SEG;
+            if (st == TB2_OK && out[nb] > n_norm) st = TB2_ERR_SEG_PAST_END;
+        }
+        if (st != TB2_OK) s.status = st;
+    }
+}
+
+// ===========================================================================
+// compute_base_means on the clipped signal (resquiggle.py:1185)
+// ===========================================================================
+__global__ void __launch_bounds__(ST_THREADS) k_base_means(BatchView b)
+{
+    const int r = blockIdx.x;
+    const ReadState &s = b.st[r];
+    if (!rd_active(s)) return;
+    const long long bo = b.base_off[r];
+    const int nb = (int)(b.base_off[r + 1] - bo);
+    const double *norm = b.norm + b.raw_off[r] + s.rsrtr;
+    const int *segs = b.segs + bo + r;
+    for (int i = threadIdx.x; i < nb; i += ST_THREADS) {
+        const int a = segs[i], z = segs[i + 1];
+        double acc = 0;
+        for (int k = a; k < z; ++k) acc += norm[k];
+        b.bm[bo + i] = acc / (double)(z - a);
+    }
+}
+
+// ===========================================================================
+// calc_kmer_fitted_shift_scale(method='theil_sen') tombo_stats.py:401-450 with
+// c_compute_slopes _c_helper.pyx:362-377: median of all pairwise slopes, then
+// median intercept.  Exact: slopes are recomputed, never approximated; a
+// 2048-bin histogram over a sample-derived bracket narrows the median to one
+// bin, whose members are selected exactly (generic radix select as fall-back).
+// ===========================================================================
+#define TS_MAX 1000
+#define TS_BINS 2048
+#define TS_BUF 2048
+
+struct TsSmem {
+    double ev[TS_MAX], md[TS_MAX];
+    unsigned int hist[TS_BINS + 2];
+    double buf[TS_BUF];
+    unsigned int nbuf, b1, b2, below;
+    int ok;
+};
+
+__device__ __forceinline__ double ts_slope(const TsSmem &t, int i, int j)
+{
+    // (i < j) -- combinations order, _c_helper.pyx:370-376
+    return (t.ev[i] == t.ev[j]) ? 1000.0 : (t.md[i] - t.md[j]) / (t.ev[i] - t.ev[j]);
+}
+
+template <class Fn>
+__device__ __forceinline__ void ts_for_pairs(int n, Fn fn)
+{
+    // balanced column pairing: column j holds pairs (i, j), i < j
+    const int half = (n + 1) / 2;
+    for (int c = threadIdx.x; c < half; c += ST_THREADS) {
+        const int j0 = c, j1 = n - 1 - c;
+        for (int i = 0; i < j0; ++i) fn(i, j0);
+        if (j1 != j0) for (int i = 0; i < j1; ++i) fn(i, j1);
+    }
+}
+
+__device__ __forceinline__ void ts_pair_of(long long s, int n, int *pi, int *pj)
+{
+    // inverse of the combinations enumeration index
+    double disc = (double)(2 * n - 1) * (double)(2 * n - 1) - 8.0 * (double)s;
+    int i = (int)(((double)(2 * n - 1) - sqrt(disc)) / 2.0);
+    if (i < 0) i = 0;
+    auto row_start = [&](int q) { return (long long)q * (2 * n - q - 1) / 2; };
+    while (i > 0 && row_start(i) > s) --i;
+    while (row_start(i + 1) <= s) ++i;
+    *pi = i;
+    *pj = (int)(s - row_start(i)) + i + 1;
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+k_theil_sen(BatchView b, StagePolicy pol, int first_call)
+{
+    extern __shared__ unsigned char ts_raw[];
+    TsSmem &t = *reinterpret_cast<TsSmem *>(ts_raw);
+    __shared__ SelectSmem sm;
+    const int r = blockIdx.x;
+    ReadState &s = b.st[r];
+    if (!rd_active(s)) return;
+    const int tid = threadIdx.x;
+    if (first_call && pol.skip_seq_scaling) {       // resquiggle.py:1179-1180
+        if (tid == 0) { s.changed = 0; s.shc = 0.0; s.scc = 1.0; }
+        return;
+    }
+    const long long bo = b.base_off[r];
+    const int nb = (int)(b.base_off[r + 1] - bo);
+    const double *bm = b.bm + bo, *rm = b.rm + bo;
+    int n = nb;
+    if (nb > TS_MAX) {                              // tombo_stats.py:411-416
+        n = TS_MAX;
+        const unsigned int key = pol.literal_key
+            ? pol.subsample_seed
+            : tb2_subsample_key(pol.subsample_seed, (unsigned int)r, (unsigned int)s.calls);
+        for (int i = tid; i < n; i += ST_THREADS) {
+            const int k = tb2_perm_index(i, nb, key);
+            t.ev[i] = bm[k]; t.md[i] = rm[k];
+        }
+    } else {
+        for (int i = tid; i < n; i += ST_THREADS) { t.ev[i] = bm[i]; t.md[i] = rm[i]; }
+    }
+    __syncthreads();
+    const long long Np = (long long)n * (n - 1) / 2;
+    if (Np <= 0) { if (tid == 0) s.status = TB2_ERR_UNEXPECTED; return; }
+    const bool even = (Np % 2) == 0;
+    const long long k1 = even ? Np / 2 - 1 : Np / 2;   // ranks k1 (and k1+1 if even)
+    double v1 = 0, v2 = 0;
+    bool have = false;
+    // ---- bracket from a sample of n/2 independent pairs ----
+    const int hs = n / 2;
+    if (hs >= 16) {
+        auto f_samp = [&](int i) { return ts_slope(t, i, i + hs); };
+        double lo, hi, d0;
+        tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.30), false, &lo, &d0, sm);
+        tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.70), false, &hi, &d0, sm);
+        if (hi > lo) {
+            const double inv_w = (double)TS_BINS / (hi - lo);
+            auto bin_of = [&](double v) -> int {
+                if (v < lo) return 0;                    // underflow bin
+                if (!(v < hi)) return TS_BINS + 1;       // overflow bin
+                int q = (int)((v - lo) * inv_w);
+                if (q >= TS_BINS) q = TS_BINS - 1;
+                return q + 1;
+            };
+            for (int i = tid; i < TS_BINS + 2; i += ST_THREADS) t.hist[i] = 0;
+            if (tid == 0) { t.nbuf = 0; t.ok = 0; }
+            __syncthreads();
+            ts_for_pairs(n, [&](int i, int j) { atomicAdd(&t.hist[bin_of(ts_slope(t, i, j))], 1u); });
+            __syncthreads();
+            if (tid == 0) {
+                // locate the bins holding ranks k1 and (if even) k1 + 1
+                long long cum = 0;
+                const long long kA = k1, kB = even ? k1 + 1 : k1;
+                int bA = -1, bB = -1;
+                long long belowA = 0;
+                for (int q = 0; q < TS_BINS + 2; ++q) {
+                    const long long c = t.hist[q];
+                    if (bA < 0 && kA < cum + c) { bA = q; belowA = cum; }
+                    if (bB < 0 && kB < cum + c) { bB = q; }
+                    cum += c;
+                    if (bA >= 0 && bB >= 0) break;
+                }
+                long long inrange = 0;
+                if (bA >= 1 && bB <= TS_BINS && bA >= 0 && bB >= 0) {
+                    for (int q = bA; q <= bB; ++q) inrange += t.hist[q];
+                    if (inrange <= TS_BUF) { t.ok = 1; t.b1 = bA; t.b2 = bB; t.below = (unsigned int)belowA; }
+                }
+            }
+            __syncthreads();
+            if (t.ok) {
+                const int bA = (int)t.b1, bB = (int)t.b2;
+                ts_for_pairs(n, [&](int i, int j) {
+                    const double v = ts_slope(t, i, j);
+                    const int q = bin_of(v);
+                    if (q >= bA && q <= bB) t.buf[atomicAdd(&t.nbuf, 1u)] = v;
+                });
+                __syncthreads();
+                const int nbuf = (int)t.nbuf;
+                tb2_block_select2([&](int i) { return t.buf[i]; }, PredAll(), nbuf,
+                                  (int)(k1 - (long long)t.below), even, &v1, &v2, sm);
+                have = true;
+            }
+        }
+    }
+    if (!have) {
+        // generic exact fall-back: radix select over all pairs
+        auto f_all = [&](int q) { int i, j; ts_pair_of(q, n, &i, &j); return ts_slope(t, i, j); };
+        tb2_block_select2(f_all, PredAll(), (int)Np, (int)k1, even, &v1, &v2, sm);
+    }
+    const double slope = even ? (v1 + v2) / 2.0 : v1;                    // np.median (:418)
+    const double inter = tb2_block_median([&](int i) { return t.md[i] - (slope * t.ev[i]); }, n, sm);  // :419
+    if (tid == 0) {
+        if (slope == 0) { s.status = TB2_ERR_THEIL_SEN_ZERO; return; }
+        const double scc = 1 / slope;
+        const double shc = -inter / slope;
+        const double shift = s.sv.shift + (shc * s.sv.scale);            // :447
+        const double scale = s.sv.scale * scc;                           // :448
+        s.sv.shift = shift; s.sv.scale = scale; s.sv.outlier_thresh = pol.outlier_thresh;
+        s.shc = shc; s.scc = scc;
+        s.changed = (fabs(shc) > 0.1) || (fabs(scc - 1) > 0.1);         // resquiggle.py:1193-1195
+    }
+}
+
+// ===========================================================================
+// final re-normalisation + per-base means + sig_match_score
+// (resquiggle.py:1190-1199, get_read_seg_score tombo_stats.py:2327-2338)
+// ===========================================================================
+__global__ void __launch_bounds__(ST_THREADS)
+k_finalize(BatchView b, StagePolicy pol, int first_call, double *norm_mean_out,
+           double *norm_signal_out)
+{
+    const int r = blockIdx.x;
+    ReadState &s = b.st[r];
+    if (!rd_active(s)) return;
+    const long long bo = b.base_off[r];
+    const int nb = (int)(b.base_off[r + 1] - bo);
+    const double *norm = b.norm + b.raw_off[r] + s.rsrtr;
+    const int *segs = b.segs + bo + r;
+    const bool rescale = !(first_call && pol.skip_seq_scaling);
+    const double shc = s.shc, scc = s.scc;
+    double *t = b.tmp_b + bo + r;
+    for (int i = threadIdx.x; i < nb; i += ST_THREADS) {
+        const int a = segs[i], z = segs[i + 1];
+        double acc = 0;
+        if (rescale) for (int k = a; k < z; ++k) acc += (norm[k] - shc) / scc;
+        else for (int k = a; k < z; ++k) acc += norm[k];
+        const double mean = acc / (double)(z - a);
+        b.bm[bo + i] = mean;
+        if (norm_mean_out) norm_mean_out[bo + i] = mean;
+        t[i] = fabs((mean - b.rm[bo + i]) / b.rs[bo + i]);
+    }
+    if (norm_signal_out) {
+        double *o = norm_signal_out + b.raw_off[r];
+        const int nn = s.n_norm;
+        for (int k = threadIdx.x; k < nn; k += ST_THREADS)
+            o[k] = rescale ? (norm[k] - shc) / scc : norm[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s.score = tb2_pairwise_sum(t, nb) / (double)nb;
+}
+
+// ===========================================================================
+// launch wrappers
+// ===========================================================================
+static inline int grid1d(int n, int bs) { return (n + bs - 1) / bs; }
+
+int tb2_launch_prep(tb2_ctx *ctx, const BatchView &b, const void *raw_dev, int raw_dtype,
+                    int is_rna, long long, long long)
+{
+    if (raw_dtype == 0)
+        k_prep<double><<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(
+            b, (const double *)raw_dev, is_rna, ctx->model_means.as<double>(),
+            ctx->model_sds.as<double>());
+    else
+        k_prep<short><<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(
+            b, (const short *)raw_dev, is_rna, ctx->model_means.as<double>(),
+            ctx->model_sds.as<double>());
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_start_attempt(tb2_ctx *ctx, const BatchView &b, int attempt)
+{
+    k_start_attempt<<<grid1d(b.n_reads, 256), 256, 0, ctx->stream>>>(b, attempt);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_begin_call(tb2_ctx *ctx, const BatchView &b, const tb2_params &p,
+                          const StagePolicy &pol)
+{
+    k_begin_call<<<grid1d(b.n_reads, 256), 256, 0, ctx->stream>>>(b, p, pol);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_end_call(tb2_ctx *ctx, const BatchView &b, int max_iters)
+{
+    k_end_call<<<grid1d(b.n_reads, 256), 256, 0, ctx->stream>>>(b, max_iters);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_count_active(tb2_ctx *ctx, const BatchView &b, int *dev_counter)
+{
+    TB2_CUDA_TRY(ctx, cudaMemsetAsync(dev_counter, 0, 2 * sizeof(int), ctx->stream));
+    k_count_active<<<grid1d(b.n_reads, 256), 256, 0, ctx->stream>>>(b, dev_counter);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_normalize(tb2_ctx *ctx, const BatchView &b, const StagePolicy &pol, int first_call)
+{
+    k_normalize<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b, pol, first_call);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_cpts(tb2_ctx *ctx, const BatchView &b, const tb2_params &p, int on_raw)
+{
+    k_cpts<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b, p, on_raw);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_rna_scale(tb2_ctx *ctx, const BatchView &b, const StagePolicy &pol)
+{
+    k_rna_scale<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b, pol);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_event_means(tb2_ctx *ctx, const BatchView &b)
+{
+    k_event_means<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_stalls(tb2_ctx *ctx, const BatchView &b)
+{
+    k_stalls<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_resolve(tb2_ctx *ctx, const BatchView &b, const tb2_params &p,
+                       const StagePolicy &pol, size_t cap)
+{
+    enum { SLOT_RAWDP = 43, SLOT_CNT2 = 44 };
+    const int warps_per_block = 4;
+    int grid = ctx->sm_count * 8;
+    const int max_useful = (b.n_reads + warps_per_block - 1) / warps_per_block;
+    if (grid > max_useful) grid = max_useful > 0 ? max_useful : 1;
+    const size_t slots = (size_t)grid * warps_per_block;
+    TB2_CUDA_TRY(ctx, ctx->pool[SLOT_RAWDP].reserve(slots * cap * sizeof(double)));
+    TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT2].reserve(sizeof(int)));
+    TB2_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool[SLOT_CNT2].p, 0, sizeof(int), ctx->stream));
+    k_resolve<<<grid, warps_per_block * 32, 0, ctx->stream>>>(
+        b, p, pol, ctx->pool[SLOT_RAWDP].as<double>(), cap, ctx->pool[SLOT_CNT2].as<int>());
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_base_means(tb2_ctx *ctx, const BatchView &b)
+{
+    k_base_means<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_theil_sen(tb2_ctx *ctx, const BatchView &b, const StagePolicy &pol, int first_call)
+{
+    const size_t smem = sizeof(TsSmem);
+    TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(k_theil_sen, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    k_theil_sen<<<b.n_reads, ST_THREADS, smem, ctx->stream>>>(b, pol, first_call);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+int tb2_launch_finalize(tb2_ctx *ctx, const BatchView &b, const StagePolicy &pol, int first_call,
+                        double *norm_mean_out, double *norm_signal_out)
+{
+    k_finalize<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b, pol, first_call, norm_mean_out,
+                                                          norm_signal_out);
+    TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
