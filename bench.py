@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py -- resquiggle throughput of the B200-native hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One step = one pass of the hot path (normalise -> segment -> banded DP -> skipped
+bases -> Theil-Sen rescale -> score, incl. the iterate / rescue policy) over one
+batch of synthetic reads.  Workload at N = 1: BASELINE.json configs[1] (100k
+synthetic DNA reads, ~4k samples, bandwidth 200, default start parameters -> every
+read takes the static-band path, W ~ 748).  For N > 1 every rank runs its own batch
+of the same size (reads shard with no collective; "scaling": "weak").
+
+Printed JSON (rank 0): `value` = reads/s with inputs resident in HBM, `e2e` = the
+same through tb2_resquiggle_batch with pinned HOST buffers (H2D + D2H inside the
+timed region), `roofline` for the dominant kernel (k_align, the banded DP) from
+CUDA-event time measured inside the library on the launching stream, `cpu_baseline`
+= the reference's own code (oracle/_ref) -- or the C port when that is absent --
+timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+ALN_DNA = (4.2, 4.2, 200, 1500, 20.0, 40, 750, 2500, 250)   # configs[1]: bandwidth = 200
+SEG_DNA = (5, 3, 1, 5)
+N_BASES = 444          # ~4k raw samples at 9 samples / base (+150 leader)
+METRIC = 'resquiggle_reads_per_sec'
+
+
+class RP(object):
+    def __init__(self, aln=ALN_DNA, seg=SEG_DNA, save=False):
+        (self.match_evalue, self.skip_pen, bw, sbw, self.max_half_z_score,
+         self.band_bound_thresh, self.start_bw, self.start_save_bw, self.start_n_bases) = aln
+        self.bandwidth = sbw if save else bw
+        (self.running_stat_width, self.min_obs_per_base, self.raw_min_obs_per_base,
+         self.mean_obs_per_event) = seg
+        self.z_shift = float(np.sqrt(2.0 / np.pi)) + self.match_evalue
+        self.stay_pen = self.match_evalue
+        self.use_t_test_seg = False
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + q,
+                                    '--format=csv,noheader,nounits'], capture_output=True,
+                                   text=True, timeout=5).stdout.strip().split('\n')[0]
+                f = [x.strip() for x in o.split(',')]
+                self.samples.append((float(f[0]), float(f[1]), f[2], f[3], f[4], f[5]))
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = []
+        for name, idx in (('hw_slowdown', 2), ('hw_thermal_slowdown', 3),
+                          ('sw_thermal_slowdown', 4), ('sw_power_cap', 5)):
+            if any(s[idx] == 'Active' for s in self.samples):
+                reasons.append(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.samples[0][1],
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------
+def make_workload(n_reads, seed, pinned_factory=None):
+    from tombo_b200 import synthetic as syn
+    kmer_ref, cpos = syn.make_kmer_ref('DNA', 0)
+    chunks, offs, seqs, soffs = [], [0], [], [0]
+    done, ci = 0, 0
+    while done < n_reads:
+        m = min(10000, n_reads - done)
+        raw, ro, codes, so = syn.make_read_batch(kmer_ref, m, N_BASES, seed * 1000 + ci)
+        chunks.append(raw); seqs.append(codes)
+        offs.extend((ro[1:] + offs[-1]).tolist())
+        soffs.extend((so[1:] + soffs[-1]).tolist())
+        done += m; ci += 1
+    raw_off = np.array(offs, dtype=np.int64)
+    seq_off = np.array(soffs, dtype=np.int64)
+    total = int(raw_off[-1])
+    if pinned_factory is not None:
+        raw = pinned_factory(total, np.float64)
+    else:
+        raw = np.empty(total)
+    p = 0
+    for c in chunks:
+        raw[p:p + c.shape[0]] = c
+        p += c.shape[0]
+    seq = np.concatenate(seqs)
+    return kmer_ref, cpos, raw, raw_off, seq, seq_off
+
+
+def dp_algorithmic_bytes(raw_off, seq_off, k, rp):
+    """A_dp = 8*E + 16*B + 8*B + 8*(B+1) + ceil(2*C/8) per read
+    (event means in, levels in, band starts + traceback out, 2-bit moves leaving
+    the chip); C = cells of the static band (n_bases x W)."""
+    s = (raw_off[1:] - raw_off[:-1]).astype(np.int64)
+    b = (seq_off[1:] - seq_off[:-1]).astype(np.int64) - (k - 1)
+    e = np.maximum(s // rp.mean_obs_per_event, (b * 1.1).astype(np.int64))
+    n_em = e - 1
+    mask = np.minimum(b, n_em) // 4
+    w = n_em - mask
+    cells = b * w
+    a = 8 * e + 16 * b + 8 * b + 8 * (b + 1) + (2 * cells + 7) // 8
+    return a.astype(np.float64), cells.astype(np.float64)
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the reference's own implementation on the host cores
+# ---------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(kind):
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    from tombo_b200 import synthetic as syn
+    kmer_ref, cpos = syn.make_kmer_ref('DNA', 0)
+    _W['kmer_ref'], _W['cpos'], _W['kind'] = kmer_ref, cpos, kind
+    if kind == 'reference':
+        import ref_harness as rh
+        _W['rh'] = rh
+        _W['std_ref'], _ = rh.make_models(kmer_ref, cpos)
+        _W['sst'], _W['p'], _W['sp'] = rh.make_params('DNA', ALN_DNA)
+    else:
+        import oracle as orc
+        _W['orc'] = orc
+        _W['means'], _W['sds'] = syn.kmer_table(kmer_ref)
+        _W['p'], _W['sp'] = RP(), RP(save=True)
+        _W['pol'] = orc.policy('DNA')
+
+
+def _cpu_one(seed):
+    from tombo_b200 import synthetic as syn
+    r = syn.make_read(_W['kmer_ref'], _W['cpos'], N_BASES, seed)
+    t0 = time.perf_counter()
+    if _W['kind'] == 'reference':
+        res, err, info = _W['rh'].run_read(r.raw, r.genome_seq, _W['std_ref'], _W['sst'],
+                                           _W['p'], _W['sp'], read_index=seed)
+        ok = res is not None
+    else:
+        codes = syn.seq_to_codes(r.genome_seq).astype(np.int64)
+        nb = codes.shape[0] - 5
+        kidx = np.zeros(nb, dtype=np.int64)
+        for j in range(6):
+            kidx = kidx * 4 + codes[j:j + nb]
+        o = _W['orc'].run_read(r.raw, _W['means'][kidx], _W['sds'][kidx], _W['p'], _W['sp'],
+                               _W['pol'], read_index=seed)
+        ok = o['status'] == 0
+    return time.perf_counter() - t0, r.raw.shape[0], ok
+
+
+def cpu_baseline_kind():
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    try:
+        import ref_harness as rh
+        if rh.available():
+            return 'reference'
+    except Exception:
+        pass
+    return 'port'
+
+
+def run_cpu(n_reads, cores, kind, seed0=900000):
+    """reads/s of the CPU implementation with `cores` worker processes
+    (multiprocessing.Pool == the compute half of the reference's --processes)."""
+    import multiprocessing as mp
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(kind,)) as pool:
+        pool.map(_cpu_one, range(seed0, seed0 + cores))          # import + warm-up
+        t0 = time.perf_counter()
+        out = pool.map(_cpu_one, range(seed0 + cores, seed0 + cores + n_reads),
+                       chunksize=max(1, n_reads // (cores * 8)))
+        wall = time.perf_counter() - t0
+    samples = sum(o[1] for o in out)
+    return {'reads_per_s': n_reads / wall, 'samples_per_s': samples / wall, 'wall_s': wall,
+            'ok': sum(o[2] for o in out), 'n': n_reads,
+            'per_read_core_ms': 1e3 * sum(o[0] for o in out) / n_reads}
+
+
+# ---------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist_mod.init_process_group(backend='gloo', rank=rank, world_size=world)
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def reduce_max(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def reduce_sum(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--reads', type=int, default=100000, help='reads per GPU per step')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='reads of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank, world, local, dist = dist_setup(args.gpus)
+    cores = host_cores()
+    workload = ('configs[1]: %d synthetic DNA reads/GPU x ~4k samples (444 bases, 6-mer model), '
+                'bandwidth=200, default start params => static-band path W~748, float64 raw'
+                % args.reads)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        kind = cpu_baseline_kind()
+        n = args.cpu_sample or cores * 24
+        for _ in range(max(0, args.warmup - 1)):
+            run_cpu(cores * 2, cores, kind)
+        t0 = time.perf_counter()
+        rs = [run_cpu(n, cores, kind, seed0=910000 + 7919 * i) for i in range(args.steps)]
+        wall = time.perf_counter() - t0
+        rps = sum(r['n'] for r in rs) / sum(r['wall_s'] for r in rs)
+        sps = sum(r['samples_per_s'] * r['wall_s'] for r in rs) / sum(r['wall_s'] for r in rs)
+        line = {
+            'impl': 'reference', 'metric': METRIC, 'value': rps, 'unit': 'reads/s',
+            'samples_per_sec': sps, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(1, args.steps),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': workload, 'reads_per_step': n, 'l2': 'n/a (CPU)'},
+            'cpu_baseline': {'value': rps, 'unit': 'reads/s', 'cores': cores, 'kind': kind,
+                             'sample': '%d reads per step, Pool(%d) over '
+                                       'resquiggle_read + iterate/rescue policy' % (n, cores)},
+            'e2e': {'value': rps, 'unit': 'reads/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ---------------- ours ----------------
+    from tombo_b200 import _lib, synthetic as syn
+    ctx = _lib.Context(local)
+    pinned = []
+
+    def pin(n, dt):
+        pa = _lib.PinnedArray((n,), dt)
+        pinned.append(pa)
+        return pa.array
+    kmer_ref, cpos, raw, raw_off, seq, seq_off = make_workload(args.reads, 1 + rank, pin)
+    means, sds = syn.kmer_table(kmer_ref)
+    ctx.set_model(means, sds, 6, cpos)
+    rp, sp = RP(), RP(save=True)
+    pol = _lib.make_policy('DNA', subsample_seed=rank)
+    n_reads = raw_off.shape[0] - 1
+    n_samples = int(raw_off[-1])
+    # pinned outputs
+    nb_tot = int((seq_off[-1]) - 5 * n_reads)
+    out = {'segs': pin(nb_tot + n_reads, np.int64), 'read_start_rel_to_raw': pin(n_reads, np.int64),
+           'scale_values': pin(n_reads * 5, np.float64).reshape(n_reads, 5),
+           'sig_match_score': pin(n_reads, np.float64), 'norm_mean': pin(nb_tot, np.float64),
+           'status': pin(n_reads, np.int32), 'n_iters': pin(n_reads, np.int32),
+           'flags': pin(n_reads, np.int32)}
+    h2d = raw.nbytes + seq.nbytes + raw_off.nbytes + seq_off.nbytes
+    d2h = sum(v.nbytes for v in out.values())
+
+    # warm-up: full end-to-end steps
+    for _ in range(max(0, args.warmup)):
+        ctx.resquiggle_batch(raw, raw_off, seq, seq_off, rp, sp, pol, out=out)
+    launches0 = ctx.launch_count()
+
+    # ---- timed region A: inputs resident in HBM (kernel path only) ----
+    ctx.batch_upload(raw, raw_off, seq, seq_off, rp, pol)
+    sampler = ClockSampler(local)
+    barrier(dist)
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = dp_ms = dp_reads = dp_launches = 0.0
+    for _ in range(args.steps):
+        ctx.batch_compute(rp, sp, pol)
+        tm = ctx.last_timing()
+        dev_ms += tm[0]; dp_ms += tm[1]; dp_launches += tm[2]; dp_reads += tm[3]
+    t_res = time.perf_counter() - t0
+    barrier(dist)
+    clocks = sampler.stop()
+    launches_timed = ctx.launch_count() - launches0
+    ctx.batch_download(out=out)
+    n_ok = int((out['status'] == 0).sum())
+
+    # ---- timed region B: end to end through the C ABI with host buffers ----
+    barrier(dist)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.resquiggle_batch(raw, raw_off, seq, seq_off, rp, sp, pol, out=out)
+    t_e2e = time.perf_counter() - t0
+    barrier(dist)
+
+    # device time is the clock of record; wall clock is reported beside it
+    t_dev = reduce_max(dist, dev_ms / 1e3)
+    t_res_w = reduce_max(dist, t_res)
+    t_e2e_w = reduce_max(dist, t_e2e)
+    tot_reads = reduce_sum(dist, float(n_reads)) * args.steps
+    tot_samples = reduce_sum(dist, float(n_samples)) * args.steps
+    tot_ok = reduce_sum(dist, float(n_ok))
+    a_dp, cells = dp_algorithmic_bytes(raw_off, seq_off, 6, rp)
+    if rank == 0:
+        peak, peak_src = peaks()
+        # every launch processes whole reads of this uniform workload
+        bytes_per_read = float(a_dp.mean())
+        dp_bytes = bytes_per_read * dp_reads
+        ach = dp_bytes / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(REPO, 'profiles', 'k_align_traffic.json')
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+            except Exception:
+                traffic = None
+        line = {
+            'metric': METRIC, 'value': tot_reads / t_dev, 'unit': 'reads/s',
+            'samples_per_sec': tot_samples / t_dev,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload, 'reads_per_gpu': n_reads,
+                       'parallelism': 'reads sharded over %d GPU(s), no collective' % args.gpus,
+                       'l2': 'inputs %.1f GB per step >> 126 MB L2 (no flush needed)'
+                             % (raw.nbytes / 1e9),
+                       'value_wall_clock_reads_per_s': tot_reads / t_res_w,
+                       'reads_ok_frac': tot_ok / (tot_reads / args.steps)},
+            'roofline': {'bound': 'hbm', 'kernel': 'k_align (banded DP + traceback)',
+                         'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                         'frac': ach / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_read': bytes_per_read,
+                         'launches': dp_launches, 'avg_launch_ms': dp_ms / max(1.0, dp_launches),
+                         'dp_share_of_step': dp_ms / max(1e-9, dev_ms),
+                         'cell_updates_per_s': float(cells.mean()) * dp_reads / (dp_ms / 1e3)
+                         if dp_ms > 0 else 0.0},
+            'e2e': {'value': tot_reads / t_e2e_w, 'unit': 'reads/s',
+                    'samples_per_sec': tot_samples / t_e2e_w,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches_timed),
+            'clocks': clocks,
+        }
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            kind = cpu_baseline_kind()
+            n = args.cpu_sample or cores * 48
+            cb = run_cpu(n, cores, kind)
+            line['cpu_baseline'] = {
+                'value': cb['reads_per_s'], 'unit': 'reads/s', 'cores': cores, 'kind': kind,
+                'samples_per_sec': cb['samples_per_s'],
+                'per_read_core_ms': cb['per_read_core_ms'],
+                'sample': '%d reads of the same workload, Pool(%d), %.1f s wall'
+                          % (n, cores, cb['wall_s'])}
+        print(json.dumps(line))
+    for pa in pinned:
+        pa.free()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

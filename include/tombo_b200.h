@@ -106,9 +106,15 @@ const char *tb2_status_message(int status);
 const char *tb2_last_error(tb2_ctx *ctx);
 /* kernels launched by this ctx since creation (bench.py "gpu_launches") */
 int64_t tb2_launch_count(tb2_ctx *ctx);
-/* device time (ms, CUDA events on the ctx stream) of the last batched call:
- * out[0] total, out[1] dominant DP kernel, out[2] number of DP launches */
-int tb2_last_timing(tb2_ctx *ctx, double *out3);
+/* device time (ms, CUDA events on the ctx stream) of the last tb2_batch_compute:
+ * out[0] whole compute stage, out[1] sum over launches of the dominant kernel
+ * (banded DP, k_align), out[2] number of k_align launches, out[3] reads
+ * processed summed over those launches */
+int tb2_last_timing(tb2_ctx *ctx, double *out4);
+
+/* page-locked host buffers (optional; any host memory is accepted by all calls) */
+void *tb2_host_alloc(size_t bytes);
+void tb2_host_free(void *p);
 
 /* ---- k-mer model (TomboModel / AltModel tables) ----------------------- */
 /* Dense table indexed by base-4 k-mer code (A=0,C=1,G=2,T=3, first base most
@@ -183,6 +189,10 @@ int tb2_find_adaptive_base_assignment(
     const double *ref_means, const double *ref_sds, int64_t n_bases,
     double sig_match_thresh, int64_t *segs_out, int64_t *read_start_rel_to_raw,
     int64_t *dbg, int *read_status);
+/* debug aid for parity tests: band event starts (n_bases) and event-space
+ * traceback (n_bases + 1) left by the last tb2_find_adaptive_base_assignment */
+int tb2_debug_last_assignment(tb2_ctx *ctx, int64_t n_bases, int64_t *starts_out,
+                              int64_t *read_tb_out);
 /* resolve_skipped_bases_with_raw resquiggle.py:402-540 */
 int tb2_resolve_skipped_bases_with_raw(
     tb2_ctx *ctx, const int64_t *segs, int64_t n_bases, const double *ref_means,
@@ -215,6 +225,22 @@ int tb2_resquiggle_batch(
     const tb2_policy *policy, int64_t *segs, int64_t *read_start_rel_to_raw,
     tb2_scale_values *scale_out, double *sig_match_score, double *norm_mean,
     double *norm_signal, int32_t *status, int32_t *n_iters, int32_t *flags);
+
+/* The same call in three stages, for callers that keep inputs resident in HBM or
+ * overlap transfers themselves: upload (H2D of raw / seq, allocation), compute
+ * (kernels only, results stay on the device), download (D2H into caller buffers
+ * laid out as in tb2_resquiggle_batch).  compute may be repeated on one upload. */
+int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
+                     const int64_t *raw_off, const uint8_t *seq,
+                     const int64_t *seq_off, const tb2_params *params,
+                     const tb2_policy *policy);
+int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
+                      const tb2_params *save_params, const tb2_policy *policy,
+                      int want_norm_signal);
+int tb2_batch_download(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_rel_to_raw,
+                       tb2_scale_values *scale_out, double *sig_match_score,
+                       double *norm_mean, double *norm_signal, int32_t *status,
+                       int32_t *n_iters, int32_t *flags);
 
 /* compute_alt_model_read_stats tombo_stats.py:3972-4082 for whole reads
  * (reg_data=None, '+' strand read-centric data), default

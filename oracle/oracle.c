@@ -825,6 +825,11 @@ static int short_read_results(const i64 *cpts, const double *em, i64 n_em, const
     return st;
 }
 
+/* debug taps for parity tests (band starts / event traceback of the last
+ * adaptive assignment) */
+static i64 *g_dbg_es = NULL, *g_dbg_tb = NULL;
+void orc_set_debug_buffers(i64 *es, i64 *tb) { g_dbg_es = es; g_dbg_tb = tb; }
+
 /* find_adaptive_base_assignment resquiggle.py:866-1050 (start_clip_bases=None) */
 int orc_find_adaptive_base_assignment(const i64 *cpts, i64 n_cpts, const double *em,
                                       const orc_params *p, const double *rm, const double *rs,
@@ -871,6 +876,8 @@ int orc_find_adaptive_base_assignment(const i64 *cpts, i64 n_cpts, const double 
         i64 top = argmax_first(fwd + nb * bw, bw);                        /* :1032 */
         st = orc_banded_traceback(tb, es, nb, bw, top, p->band_bound_thresh, tbk);
     }
+    if (g_dbg_es) memcpy(g_dbg_es, es, sizeof(i64) * (size_t)nb);
+    if (st == ORC_OK && g_dbg_tb) memcpy(g_dbg_tb, tbk, sizeof(i64) * (size_t)(nb + 1));
     if (st == ORC_OK) {
         /* _trim_traceback :754-764 */
         i64 i = 0;

@@ -159,6 +159,7 @@ int orc_find_adaptive_base_assignment(
     i64 *dbg_path /* may be NULL: [0]=0 static,1 adaptive; [1]=mapped_start;
                      [2]=events_start_clip */,
     double *dbg_epb /* may be NULL */);
+void orc_set_debug_buffers(i64 *es, i64 *tb);
 int orc_resolve_skipped_bases_with_raw(
     const i64 *segs, i64 nb, const double *rm, const double *rs,
     const double *norm, i64 n_norm, const orc_params *p, i64 max_raw_cpts,

@@ -83,6 +83,30 @@ def status_message(st):
     return load().tb2_status_message(int(st)).decode()
 
 
+class PinnedArray(object):
+    """numpy array backed by page-locked host memory (tb2_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        lib = load()
+        lib.tb2_host_alloc.restype = C.c_void_p
+        lib.tb2_host_alloc.argtypes = [C.c_size_t]
+        lib.tb2_host_free.argtypes = [C.c_void_p]
+        self._lib = lib
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape))
+        self._p = lib.tb2_host_alloc(max(1, n * dt.itemsize))
+        if not self._p:
+            raise TomboB200Error('tb2_host_alloc failed (no CUDA device?)')
+        buf = (C.c_char * (n * dt.itemsize)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self._lib.tb2_host_free(C.c_void_p(self._p))
+            self._p = None
+
+
 def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -149,9 +173,72 @@ class Context(object):
         return int(self.lib.tb2_launch_count(self.handle))
 
     def last_timing(self):
-        out = (f64 * 3)()
+        """(compute ms, DP-kernel ms, DP launches, reads summed over DP launches)"""
+        out = (f64 * 4)()
         self.lib.tb2_last_timing(self.handle, out)
         return tuple(out)
+
+    # ---- staged batch API (resident inputs) --------------------------------
+    def batch_upload(self, raw, raw_off, seq, seq_off, params, policy):
+        raw = np.ascontiguousarray(raw)
+        dtype = 1 if raw.dtype == np.int16 else 0
+        if dtype == 0:
+            raw = as_f64(raw)
+        raw_off, seq_off = as_i64(raw_off), as_i64(seq_off)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        p = params if isinstance(params, Params) else params_struct(params)
+        fn = self.lib.tb2_batch_upload
+        fn.restype = C.c_int
+        self.check(fn(self.handle, i64(raw_off.shape[0] - 1),
+                      raw.ctypes.data_as(C.c_void_p), C.c_int(dtype),
+                      ptr(raw_off, i64), ptr(seq, C.c_uint8), ptr(seq_off, i64),
+                      C.byref(p), C.byref(policy)))
+        k = self.kmer_width
+        n = raw_off.shape[0] - 1
+        nb = (seq_off[1:] - seq_off[:-1]) - (k - 1)
+        self._base_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        self._seg_off = self._base_off + np.arange(n + 1, dtype=np.int64)
+        self._n_samples = int(raw_off[-1])
+
+    def batch_compute(self, params, save_params, policy, want_norm_signal=False):
+        p = params if isinstance(params, Params) else params_struct(params)
+        sp = None
+        if save_params is not None:
+            sp = save_params if isinstance(save_params, Params) else params_struct(save_params)
+        fn = self.lib.tb2_batch_compute
+        fn.restype = C.c_int
+        self.check(fn(self.handle, C.byref(p), C.byref(sp) if sp is not None else None,
+                      C.byref(policy), C.c_int(int(bool(want_norm_signal)))))
+
+    def batch_download(self, want_norm_signal=False, out=None):
+        base_off, seg_off = self._base_off, self._seg_off
+        n = base_off.shape[0] - 1
+        if out is None:
+            out = {}
+
+        def buf(name, shape, dt):
+            a = out.get(name)
+            if a is None or a.shape != tuple(np.atleast_1d(shape)) or a.dtype != dt:
+                a = out[name] = np.empty(shape, dtype=dt)
+            return a
+        segs = buf('segs', int(seg_off[-1]), np.int64)
+        rsrtr = buf('read_start_rel_to_raw', n, np.int64)
+        sv = buf('scale_values', (n, 5), np.float64)
+        score = buf('sig_match_score', n, np.float64)
+        norm_mean = buf('norm_mean', int(base_off[-1]), np.float64)
+        status = buf('status', n, np.int32)
+        n_iters = buf('n_iters', n, np.int32)
+        flags = buf('flags', n, np.int32)
+        norm_sig = buf('norm_signal', self._n_samples, np.float64) if want_norm_signal else None
+        fn = self.lib.tb2_batch_download
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(segs, i64), ptr(rsrtr, i64),
+                      sv.ctypes.data_as(C.c_void_p), ptr(score, f64), ptr(norm_mean, f64),
+                      ptr(norm_sig, f64) if norm_sig is not None else None,
+                      ptr(status, C.c_int32), ptr(n_iters, C.c_int32),
+                      ptr(flags, C.c_int32)))
+        out['base_off'], out['seg_off'] = base_off, seg_off
+        return out
 
     # ---- mirror API: _c_dynamic_programming.pyx ---------------------------
     def banded_forward_pass(self, z, event_starts, skip_pen, stay_pen):

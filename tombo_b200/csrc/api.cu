@@ -53,12 +53,29 @@ extern "C" void tb2_ctx_destroy(tb2_ctx *ctx)
 
 extern "C" const char *tb2_last_error(tb2_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
+// page-locked host memory for callers that want full-rate H2D / D2H copies
+extern "C" void *tb2_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void tb2_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int64_t tb2_launch_count(tb2_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int tb2_last_timing(tb2_ctx *ctx, double *out3)
+extern "C" int tb2_last_timing(tb2_ctx *ctx, double *out3 /* 4 values */)
 {
     if (!ctx || !out3) return TB2_ERR_INVALID_ARG;
     out3[0] = ctx->last_ms_total; out3[1] = ctx->last_ms_dp; out3[2] = ctx->last_dp_launches;
+    out3[3] = ctx->last_dp_reads;
     return TB2_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/tombo_b200.h"
@@ -39,7 +40,8 @@ struct tb2_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::string err;
     int64_t launches = 0;
-    double last_ms_total = 0, last_ms_dp = 0, last_dp_launches = 0;
+    double last_ms_total = 0, last_ms_dp = 0, last_dp_launches = 0, last_dp_reads = 0;
+    std::shared_ptr<void> batch;   // BatchHolder (pipeline.cu)
     // model tables
     DevBuf model_means, model_sds, alt_means;
     int kmer_width = 0, central_pos = 0, alt_kmer_width = 0;

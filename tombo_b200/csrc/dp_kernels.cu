@@ -421,3 +421,18 @@ extern "C" int tb2_find_adaptive_base_assignment(
     if (dbg) { dbg[0] = small[3]; dbg[1] = small[4]; dbg[2] = small[5]; }
     return TB2_OK;
 }
+
+// debug aid for parity tests: band starts and event traceback of the last
+// tb2_find_adaptive_base_assignment call on this ctx (n_bases entries / n_bases+1)
+extern "C" int tb2_debug_last_assignment(tb2_ctx *ctx, int64_t n_bases, int64_t *starts_out,
+                                         int64_t *read_tb_out)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (n_bases < 1 || !starts_out || !read_tb_out) return TB2_ERR_INVALID_ARG;
+    std::vector<int> h((size_t)(n_bases + 1) * 2);
+    TB2_CUDA_TRY(ctx, cudaMemcpy(h.data(), ctx->pool[S_F].p, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n_bases; ++i) starts_out[i] = h[i];
+    for (int64_t i = 0; i <= n_bases; ++i) read_tb_out[i] = h[(n_bases + 1) + i];
+    return TB2_OK;
+}

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 int tb2_launch_start_attempt(tb2_ctx *ctx, const BatchView &b, int attempt);
@@ -138,6 +139,13 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
                 cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(p.start_n_bases, p.start_save_bw));
                 cfg->grow_cells = std::max(cfg->grow_cells, tb2_row_cells(p.start_save_bw));
             }
+            // long reads may fall back to the static band (failed start search with
+            // too few events for the save bandwidth, or a start too close to the
+            // read end: resquiggle.py:996-999, 1024-1027); rows live in global memory
+            if (tb2_row_cells(w_static) / 32 <= 5 * 16) {
+                cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(nb, w_static));
+                cfg->grow_cells = std::max(cfg->grow_cells, tb2_row_cells(w_static));
+            }
         }
     }
 }
@@ -248,58 +256,94 @@ extern "C" int tb2_set_model(tb2_ctx *ctx, const double *means, const double *sd
     return TB2_OK;
 }
 
-extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
-                                    const int64_t *raw_off, const uint8_t *seq,
-                                    const int64_t *seq_off, const tb2_params *params,
-                                    const tb2_params *save_params, const tb2_policy *policy,
-                                    int64_t *segs, int64_t *read_start_rel_to_raw,
-                                    tb2_scale_values *scale_out, double *sig_match_score,
-                                    double *norm_mean, double *norm_signal, int32_t *status,
-                                    int32_t *n_iters, int32_t *flags)
+// ---------------------------------------------------------------------------
+// batched hot path in three stages: upload (H2D), compute (kernels only; results
+// stay on the device), download (D2H).  tb2_resquiggle_batch = all three.
+// ---------------------------------------------------------------------------
+namespace {
+struct BatchHolder {
+    HostBatch hb;
+    BatchView v;
+    std::vector<int64_t> raw_off;
+    int raw_dtype = 0;
+    bool uploaded = false, computed = false, has_norm_sig = false;
+};
+
+BatchHolder *holder_of(tb2_ctx *ctx)
+{
+    if (!ctx->batch) ctx->batch = std::shared_ptr<void>(new BatchHolder(), [](void *p) { delete (BatchHolder *)p; });
+    return (BatchHolder *)ctx->batch.get();
+}
+}  // namespace
+
+extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
+                                const int64_t *raw_off, const uint8_t *seq, const int64_t *seq_off,
+                                const tb2_params *params, const tb2_policy *policy)
 {
     int rc = tb2_use(ctx);
     if (rc) return rc;
-    if (n_reads < 0 || n_reads > 0x7ffffff0 || !raw_off || !seq_off || !params || !policy ||
-        !segs || !read_start_rel_to_raw || !scale_out || !sig_match_score || !status || !n_iters ||
-        !flags || (raw_dtype != 0 && raw_dtype != 1))
+    if (n_reads < 1 || n_reads > 0x7ffffff0 || !raw || !seq || !raw_off || !seq_off || !params ||
+        !policy || (raw_dtype != 0 && raw_dtype != 1))
         return TB2_ERR_INVALID_ARG;
-    if (n_reads == 0) return TB2_OK;
-    if (!raw || !seq) return TB2_ERR_INVALID_ARG;
     if (ctx->kmer_width <= 0) { ctx->err = "tb2_set_model has not been called"; return TB2_ERR_INVALID_ARG; }
-    if (policy->rescue && !save_params) return TB2_ERR_INVALID_ARG;
+    BatchHolder *h = holder_of(ctx);
+    h->uploaded = h->computed = false;
     const int n = (int)n_reads;
+    rc = build_view(ctx, n, raw_off, seq_off, ctx->kmer_width, *params,
+                    policy->min_event_to_seq_ratio, (int)policy->is_rna, h->hb, h->v);
+    if (rc) return rc;
+    h->raw_off.assign(raw_off, raw_off + n + 1);
+    h->raw_dtype = raw_dtype;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    const size_t esz = raw_dtype == 0 ? 8 : 2;
+    TB2_CUDA_TRY(ctx, P[B_RAWIN].reserve((size_t)h->hb.total_s * esz + 8));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_RAWIN].p, raw, (size_t)h->hb.total_s * esz, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_SEQ].p, seq, (size_t)h->hb.total_seq, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    h->uploaded = true;
+    return TB2_OK;
+}
+
+extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
+                                 const tb2_params *save_params, const tb2_policy *policy,
+                                 int want_norm_signal)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!params || !policy) return TB2_ERR_INVALID_ARG;
+    if (policy->rescue && !save_params) return TB2_ERR_INVALID_ARG;
+    BatchHolder *h = holder_of(ctx);
+    if (!h->uploaded) { ctx->err = "tb2_batch_upload has not been called"; return TB2_ERR_INVALID_ARG; }
+    h->computed = false;
     const StagePolicy sp = stage_policy(*policy);
-    HostBatch hb;
-    BatchView v;
+    const HostBatch &hb = h->hb;
+    const BatchView &v = h->v;
+    const int n = hb.n;
+    auto &P = ctx->pool;
     cudaStream_t s = ctx->stream;
     TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, s));
-    rc = build_view(ctx, n, raw_off, seq_off, ctx->kmer_width, *params, sp.min_event_to_seq_ratio,
-                    sp.is_rna, hb, v);
-    if (rc) return rc;
-    auto &P = ctx->pool;
-    const size_t esz = raw_dtype == 0 ? 8 : 2;
-    TB2_CUDA_TRY(ctx, P[B_RAWIN].reserve((size_t)hb.total_s * esz + 8));
-    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_RAWIN].p, raw, (size_t)hb.total_s * esz, cudaMemcpyHostToDevice, s));
-    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_SEQ].p, seq, (size_t)hb.total_seq, cudaMemcpyHostToDevice, s));
     TB2_CUDA_TRY(ctx, P[B_OUT_NORMMEAN].reserve((size_t)hb.total_b * 8 + 8));
     double *norm_sig_dev = nullptr;
-    if (norm_signal) {
+    if (want_norm_signal) {
         TB2_CUDA_TRY(ctx, P[B_OUT_NORMSIG].reserve((size_t)hb.total_s * 8 + 8));
         norm_sig_dev = P[B_OUT_NORMSIG].as<double>();
     }
+    h->has_norm_sig = want_norm_signal != 0;
     double *norm_mean_dev = P[B_OUT_NORMMEAN].as<double>();
-    if ((rc = tb2_launch_prep(ctx, v, P[B_RAWIN].p, raw_dtype, sp.is_rna, hb.total_s, hb.total_b))) return rc;
+    if ((rc = tb2_launch_prep(ctx, v, P[B_RAWIN].p, h->raw_dtype, sp.is_rna, hb.total_s, hb.total_b))) return rc;
     if (sp.is_rna && (rc = tb2_launch_stalls(ctx, v))) return rc;
     const size_t rawdp_cap = (size_t)1 << 15;
-    double ms_dp = 0;
+    double ms_dp = 0, dp_reads = 0;
     int dp_launches = 0;
     int counters[2] = {0, 0};
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (attempt == 1 && (!policy->rescue || counters[1] == 0)) break;
         const tb2_params &p = attempt == 0 ? *params : *save_params;
         AlignLaunchCfg acfg;
-        plan_align_batch(p, hb, raw_off, sp.min_event_to_seq_ratio, &acfg);
+        plan_align_batch(p, hb, h->raw_off.data(), sp.min_event_to_seq_ratio, &acfg);
         if ((rc = tb2_launch_start_attempt(ctx, v, attempt))) return rc;
+        double active_now = attempt == 0 ? n : counters[1];
         for (int it = 0; it < std::max(1, sp.max_scaling_iters); ++it) {
             if ((rc = run_call(ctx, v, p, sp, acfg, it == 0, norm_mean_dev, norm_sig_dev, rawdp_cap)))
                 return rc;
@@ -307,11 +351,14 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
             TB2_CUDA_TRY(ctx, cudaMemcpyAsync(counters, P[B_COUNTERS].p, 8, cudaMemcpyDeviceToHost, s));
             TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) { ms_dp += ms; ++dp_launches; }
+            if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) {
+                ms_dp += ms; ++dp_launches; dp_reads += active_now;
+            }
+            active_now = counters[0];
             if (counters[0] == 0) break;
         }
     }
-    // ---- export ----
+    // ---- export into device staging ----
     const size_t nsegs = (size_t)hb.total_b + n;
     TB2_CUDA_TRY(ctx, P[B_OUT_SEGS].reserve(nsegs * 8 + 8));
     const size_t small_bytes = (size_t)n * (8 + sizeof(tb2_scale_values) + 8 + 4 + 4 + 4);
@@ -326,6 +373,42 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
     k_export<<<n, 128, 0, s>>>(v, P[B_DBG].as<int>(), P[B_OUT_SEGS].as<long long>(), d_rs, d_sv,
                                d_score, d_status, d_iters, d_flags);
     TB2_CHECK_LAUNCH(ctx);
+    TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms_total = ms;
+    ctx->last_ms_dp = ms_dp;
+    ctx->last_dp_launches = dp_launches;
+    ctx->last_dp_reads = dp_reads;
+    h->computed = true;
+    return TB2_OK;
+}
+
+extern "C" int tb2_batch_download(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_rel_to_raw,
+                                  tb2_scale_values *scale_out, double *sig_match_score,
+                                  double *norm_mean, double *norm_signal, int32_t *status,
+                                  int32_t *n_iters, int32_t *flags)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    BatchHolder *h = holder_of(ctx);
+    if (!h->computed) { ctx->err = "tb2_batch_compute has not been called"; return TB2_ERR_INVALID_ARG; }
+    if (!segs || !read_start_rel_to_raw || !scale_out || !sig_match_score || !status || !n_iters ||
+        !flags || (norm_signal && !h->has_norm_sig))
+        return TB2_ERR_INVALID_ARG;
+    const HostBatch &hb = h->hb;
+    const int n = hb.n;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    const size_t nsegs = (size_t)hb.total_b + n;
+    unsigned char *sm = P[B_OUT_SMALL].as<unsigned char>();
+    long long *d_rs = (long long *)sm;
+    tb2_scale_values *d_sv = (tb2_scale_values *)(d_rs + n);
+    double *d_score = (double *)(d_sv + n);
+    int *d_status = (int *)(d_score + n);
+    int *d_iters = d_status + n;
+    int *d_flags = d_iters + n;
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(segs, P[B_OUT_SEGS].p, nsegs * 8, cudaMemcpyDeviceToHost, s));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(read_start_rel_to_raw, d_rs, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(scale_out, d_sv, (size_t)n * sizeof(tb2_scale_values), cudaMemcpyDeviceToHost, s));
@@ -334,17 +417,28 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(n_iters, d_iters, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(flags, d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     if (norm_mean)
-        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(norm_mean, norm_mean_dev, (size_t)hb.total_b * 8, cudaMemcpyDeviceToHost, s));
+        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(norm_mean, P[B_OUT_NORMMEAN].p, (size_t)hb.total_b * 8, cudaMemcpyDeviceToHost, s));
     if (norm_signal)
-        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(norm_signal, norm_sig_dev, (size_t)hb.total_s * 8, cudaMemcpyDeviceToHost, s));
-    TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, s));
+        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(norm_signal, P[B_OUT_NORMSIG].p, (size_t)hb.total_s * 8, cudaMemcpyDeviceToHost, s));
     TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->last_ms_total = ms;
-    ctx->last_ms_dp = ms_dp;
-    ctx->last_dp_launches = dp_launches;
     return TB2_OK;
+}
+
+extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
+                                    const int64_t *raw_off, const uint8_t *seq,
+                                    const int64_t *seq_off, const tb2_params *params,
+                                    const tb2_params *save_params, const tb2_policy *policy,
+                                    int64_t *segs, int64_t *read_start_rel_to_raw,
+                                    tb2_scale_values *scale_out, double *sig_match_score,
+                                    double *norm_mean, double *norm_signal, int32_t *status,
+                                    int32_t *n_iters, int32_t *flags)
+{
+    if (n_reads == 0) return tb2_use(ctx);
+    int rc = tb2_batch_upload(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy);
+    if (rc) return rc;
+    if ((rc = tb2_batch_compute(ctx, params, save_params, policy, norm_signal != nullptr))) return rc;
+    return tb2_batch_download(ctx, segs, read_start_rel_to_raw, scale_out, sig_match_score,
+                              norm_mean, norm_signal, status, n_iters, flags);
 }
 
 // ---------------------------------------------------------------------------

@@ -62,6 +62,8 @@ __global__ void k_start_attempt(BatchView b, int attempt)
         s.active = 1;
     } else {
         if (s.status == TB2_OK) { s.active = 0; s.done = 1; return; }  // defensive
+        // capacity overruns are library limits, not read failures: never rescued
+        if (s.status == TB2_ERR_CAPACITY) { s.active = 0; s.done = 1; return; }
         s.first_status = s.status;
         s.status = TB2_OK;
         s.active = 1;
@@ -343,7 +345,6 @@ k_cpts(BatchView b, tb2_params p, int on_raw)
     for (int i = i0; i < i1; ++i) if (keep(i)) cp[o++] = i + w;
     if (tid == 0) {
         s.n_cpts = (int)total;
-        if (total < 2) s.status = TB2_ERR_UNEXPECTED;
     }
 }
 
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_event_means(BatchView b)
     const int *cp = b.cpts + b.ev_off[r];
     double *em = b.em + b.ev_off[r];
     const int ne = s.n_cpts - 1;
+    if (ne < 1) { if (threadIdx.x == 0) b.st[r].status = TB2_ERR_UNEXPECTED; return; }
     for (int e = threadIdx.x; e < ne; e += ST_THREADS) {
         const int a = cp[e], z = cp[e + 1];
         double acc = 0;
