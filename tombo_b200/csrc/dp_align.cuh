@@ -6,7 +6,9 @@
 #pragma once
 #include "dp_row.cuh"
 
-#define TB2_MAX_WPL 5  // band widths up to 5*16*32 = 2560 cells
+// packed-move words per lane are instantiated for {1,2,3,4,5,8,16}: band widths up
+// to 16*16*32 = 8192 cells
+#define TB2_MAX_WPL 16
 #define TB2_MASK_FILL_Z_SCORE (-15.0)
 
 // per-warp resources
@@ -51,7 +53,11 @@ __device__ __forceinline__ bool tb2_setup_geom(PassCtx &pc, const WarpRes &wr, i
     return false;
 }
 
-__device__ __forceinline__ int tb2_wpl_of(int chunk) { return (chunk + 15) / 16; }
+__device__ __forceinline__ int tb2_wpl_of(int chunk)
+{
+    const int w = (chunk + 15) / 16;
+    return w <= 5 ? w : (w <= 8 ? 8 : (w <= 16 ? 16 : w));
+}
 
 __device__ int tb2_run_rows_dyn(int wpl, const PassCtx &pc, const DpConsts &c, int mode,
                                 int r_begin, int r_end, int nb_total, int *cur_sel, int *amax)
@@ -62,6 +68,8 @@ __device__ int tb2_run_rows_dyn(int wpl, const PassCtx &pc, const DpConsts &c, i
     case 3: return tb2_run_rows<3>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
     case 4: return tb2_run_rows<4>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
     case 5: return tb2_run_rows<5>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
+    case 8: return tb2_run_rows<8>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
+    case 16: return tb2_run_rows<16>(pc, c, mode, r_begin, r_end, nb_total, cur_sel, amax);
     default: return TB2_ERR_CAPACITY;
     }
 }
@@ -75,6 +83,8 @@ __device__ int tb2_traceback_dyn(int wpl, const uint32_t *tb, const int *starts,
     case 3: return tb2_traceback<3>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
     case 4: return tb2_traceback<4>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
     case 5: return tb2_traceback<5>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    case 8: return tb2_traceback<8>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    case 16: return tb2_traceback<16>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
     default: return TB2_ERR_CAPACITY;
     }
 }

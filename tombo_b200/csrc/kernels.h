@@ -35,10 +35,12 @@ struct AlignLaunchCfg {
 int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cfg);
 
 // capacity helper (host): packed-move words needed for (rows, W)
+#define TB2_MAX_CHUNK 256   // cells per lane: band widths up to 8192 (dp_align.cuh)
 static inline size_t tb2_tb_words(long long rows, long long W)
 {
     long long chunk = (W + 31) / 32;
     long long wpl = (chunk + 15) / 16;
+    wpl = wpl <= 5 ? wpl : (wpl <= 8 ? 8 : 16);   // instantiated widths (tb2_wpl_of)
     return (size_t)(rows * wpl * 32);
 }
 static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }

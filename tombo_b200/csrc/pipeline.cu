@@ -127,7 +127,7 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
         const long long w_static = std::max<long long>(1, n_em - mask_len);
         const bool is_short = n_em < p.start_bw + p.start_n_bases || nb < p.start_n_bases;
         if (is_short) {
-            if (tb2_row_cells(w_static) / 32 > 5 * 16) continue;  // CAPACITY status on device
+            if (tb2_row_cells(w_static) / 32 > TB2_MAX_CHUNK) continue;  // CAPACITY status on device
             cfg->smem_cells = std::max(cfg->smem_cells, tb2_row_cells(w_static));
             cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(nb, w_static));
         } else {
@@ -142,7 +142,7 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
             // long reads may fall back to the static band (failed start search with
             // too few events for the save bandwidth, or a start too close to the
             // read end: resquiggle.py:996-999, 1024-1027); rows live in global memory
-            if (tb2_row_cells(w_static) / 32 <= 5 * 16) {
+            if (tb2_row_cells(w_static) / 32 <= TB2_MAX_CHUNK) {
                 cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(nb, w_static));
                 cfg->grow_cells = std::max(cfg->grow_cells, tb2_row_cells(w_static));
             }
