@@ -141,6 +141,10 @@ int tb2_normalize_raw_signal(tb2_ctx *ctx, const double *raw, int64_t n,
                              int norm_type, double outlier_thresh,
                              double const_scale, const tb2_scale_values *sv_in,
                              double *norm_out, tb2_scale_values *sv_out);
+/* identify_stalls (mean-window method, MEAN_STALL_PARAMS) tombo_stats.py:269-368;
+ * ints_out receives n_out (start, end) pairs (capacity `cap` pairs) */
+int tb2_identify_stalls(tb2_ctx *ctx, const double *raw, int64_t n, int64_t *ints_out,
+                        int64_t cap, int64_t *n_out);
 /* c_valid_cpts_w_cap _c_helper.pyx:89-120 (+ sort, tombo_helper.py:76-82);
  * t_test != 0: c_valid_cpts_w_cap_t_test _c_helper.pyx:144-202.
  * Rank order: score descending, ties -> larger position first. */
@@ -189,6 +193,22 @@ int tb2_find_adaptive_base_assignment(
     const double *ref_means, const double *ref_sds, int64_t n_bases,
     double sig_match_thresh, int64_t *segs_out, int64_t *read_start_rel_to_raw,
     int64_t *dbg, int *read_status);
+/* find_static_base_assignment resquiggle.py:547-600: read_tb_out has n_bases + 1
+ * event positions (the th.banded_traceback result) */
+int tb2_find_static_base_assignment(tb2_ctx *ctx, const double *event_means,
+                                    int64_t n_events, const double *ref_means,
+                                    const double *ref_sds, int64_t n_bases,
+                                    const tb2_params *params, int64_t *read_tb_out,
+                                    int *read_status);
+/* find_seq_start_in_events resquiggle.py:685-752; check_score <=> seq_samp_type
+ * passed (SIG_MATCH_THRESH test, :742-746) */
+int tb2_find_seq_start_in_events(tb2_ctx *ctx, const double *event_means,
+                                 int64_t n_events, const double *ref_means,
+                                 const double *ref_sds, int64_t n_ref,
+                                 const tb2_params *params, int64_t num_bases,
+                                 int64_t num_events, int check_score,
+                                 double sig_match_thresh, int64_t *start_loc,
+                                 double *events_per_base, int *read_status);
 /* debug aid for parity tests: band event starts (n_bases) and event-space
  * traceback (n_bases + 1) left by the last tb2_find_adaptive_base_assignment */
 int tb2_debug_last_assignment(tb2_ctx *ctx, int64_t n_bases, int64_t *starts_out,
@@ -234,6 +254,11 @@ int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dty
                      const int64_t *raw_off, const uint8_t *seq,
                      const int64_t *seq_off, const tb2_params *params,
                      const tb2_policy *policy);
+/* optional, between upload and compute: per-read map_res.scale_values (sv_in[r]
+ * with NaN shift = none) and map_res.stall_ints (pairs (start, end), stall_off has
+ * n_reads + 1 entries counting pairs); either may be NULL */
+int tb2_batch_set_read_inputs(tb2_ctx *ctx, const tb2_scale_values *sv_in,
+                              const int64_t *stall_ints, const int64_t *stall_off);
 int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
                       const tb2_params *save_params, const tb2_policy *policy,
                       int want_norm_signal);
@@ -256,6 +281,18 @@ int tb2_alt_model_llr_batch(
     const int64_t *read_start, int alt_base_code, int use_standard_llhr,
     double scale_factor, double height_factor, double height_power,
     double *llr_out, int64_t *pos_out, int64_t *site_off);
+
+/* The three Cython scorers batched over explicit windows (n_sites x kmer_width,
+ * row-major): mode 0 c_calc_scaled_llh_ratio_const_var (_c_helper.pyx:313-358),
+ * mode 1 c_calc_llh_ratio_const_var (:298-311), mode 2 c_calc_llh_ratio (:277-296).
+ * var_a = const_var[n_sites] (modes 0, 1) or ref_vars[n_sites x K] (mode 2);
+ * var_b = alt_vars[n_sites x K] (mode 2 only). */
+int tb2_calc_llh_ratio_windows(tb2_ctx *ctx, int mode, int64_t n_sites, int kmer_width,
+                               const double *means, const double *ref_means,
+                               const double *alt_means, const double *var_a,
+                               const double *var_b, double scale_factor,
+                               double height_factor, double height_power,
+                               double *llr_out);
 
 #ifdef __cplusplus
 }

@@ -38,3 +38,48 @@ def test_no_cpu_fallback_without_device():
         pytest.skip('a device is present')
     with pytest.raises(_lib.TomboB200Error):
         _lib.Context(0)
+
+
+def test_python_api_surface_imports_without_gpu():
+    from tombo_b200 import tombo_helper as th, tombo_stats as ts, resquiggle as rsq
+    for name in ('resquiggle_read', 'segment_signal', 'find_adaptive_base_assignment',
+                 'resolve_skipped_bases_with_raw', 'find_seq_start_in_events',
+                 'find_static_base_assignment', 'resquiggle_reads'):
+        assert callable(getattr(rsq, name))
+    for name in ('TomboModel', 'AltModel', 'normalize_raw_signal', 'compute_base_means',
+                 'get_read_seg_score', 'calc_kmer_fitted_shift_scale',
+                 'load_resquiggle_parameters', 'compute_num_events',
+                 'compute_alt_model_read_stats'):
+        assert hasattr(ts, name)
+    p = ts.load_resquiggle_parameters(th.seqSampleType('DNA', False))
+    assert p.bandwidth == 300 and p.start_bw == 750 and p.z_shift > 4.99
+    sp = ts.load_resquiggle_parameters(th.seqSampleType('RNA', True), use_save_bandwidth=True)
+    assert sp.bandwidth == 1500 and sp.use_t_test_seg
+    assert ts.compute_num_events(4300, 444, 5) == 860
+    m = th.TomboMotif('CCWGG', 2)
+    assert m.motif_pat.pattern == 'CC[AT]GG' and m.mod_base == 'C'
+
+
+def test_parameters_and_namedtuples_match_reference_when_available():
+    import sys, os
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import ref_harness as rh
+    if not rh.available():
+        pytest.skip('oracle/_ref not built')
+    m = rh.load_reference()
+    from tombo_b200 import tombo_helper as th, tombo_stats as ts, _default_parameters as dp
+    import tombo._default_parameters as rdp
+    for name in dir(dp):
+        if name.isupper():
+            assert getattr(dp, name) == getattr(rdp, name), name
+    for nt in ('alignInfo', 'readData', 'scaleValues', 'resquiggleParams', 'resquiggleResults',
+               'dpResults', 'genomeLocation', 'seqSampleType', 'stallParams', 'channelInfo'):
+        assert getattr(th, nt)._fields == getattr(m['th'], nt)._fields, nt
+    for kind in ('DNA', 'RNA'):
+        sst = th.seqSampleType(kind, kind == 'RNA')
+        for save in (False, True):
+            a = ts.load_resquiggle_parameters(sst, use_save_bandwidth=save)
+            b = m['ts'].load_resquiggle_parameters(m['th'].seqSampleType(kind, kind == 'RNA'),
+                                                   use_save_bandwidth=save)
+            assert tuple(a) == tuple(b)
+    assert ts.HALF_NORM_EXPECTED_VAL == m['ts'].HALF_NORM_EXPECTED_VAL

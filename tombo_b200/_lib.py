@@ -402,6 +402,79 @@ class Context(object):
                       ptr(out, i64), C.byref(st)))
         return st.value, out
 
+    def identify_stalls(self, raw):
+        raw = as_f64(raw)
+        cap = raw.shape[0] // 200 + 4
+        out = np.empty(2 * cap, dtype=np.int64)
+        n = i64(0)
+        fn = self.lib.tb2_identify_stalls
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(raw, f64), i64(raw.shape[0]), ptr(out, i64),
+                      i64(cap), C.byref(n)))
+        return out[:2 * n.value].reshape(-1, 2).copy()
+
+    def calc_llh_ratio_windows(self, mode, means, ref_means, alt_means, var_a, var_b=None,
+                               scale_factor=4.0, height_factor=1.0, height_power=0.2):
+        means, ref_means, alt_means = as_f64(means), as_f64(ref_means), as_f64(alt_means)
+        var_a = as_f64(var_a)
+        n, k = means.shape
+        out = np.empty(n)
+        vb = as_f64(var_b) if var_b is not None else None
+        fn = self.lib.tb2_calc_llh_ratio_windows
+        fn.restype = C.c_int
+        self.check(fn(self.handle, C.c_int(mode), i64(n), C.c_int(k), ptr(means, f64),
+                      ptr(ref_means, f64), ptr(alt_means, f64), ptr(var_a, f64),
+                      ptr(vb, f64) if vb is not None else None, f64(scale_factor),
+                      f64(height_factor), f64(height_power), ptr(out, f64)))
+        return out
+
+    def find_static_base_assignment(self, event_means, rm, rs, params):
+        em, rm, rs = as_f64(event_means), as_f64(rm), as_f64(rs)
+        out = np.empty(rm.shape[0] + 1, dtype=np.int64)
+        st = C.c_int(0)
+        p = params if isinstance(params, Params) else params_struct(params)
+        fn = self.lib.tb2_find_static_base_assignment
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(em, f64), i64(em.shape[0]), ptr(rm, f64), ptr(rs, f64),
+                      i64(rm.shape[0]), C.byref(p), ptr(out, i64), C.byref(st)))
+        return st.value, out
+
+    def find_seq_start_in_events(self, event_means, rm, rs, params, num_bases, num_events,
+                                 sig_match_thresh=None):
+        em, rm, rs = as_f64(event_means), as_f64(rm), as_f64(rs)
+        st, sl, epb = C.c_int(0), i64(0), f64(0)
+        p = params if isinstance(params, Params) else params_struct(params)
+        fn = self.lib.tb2_find_seq_start_in_events
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(em, f64), i64(em.shape[0]), ptr(rm, f64), ptr(rs, f64),
+                      i64(rm.shape[0]), C.byref(p), i64(num_bases), i64(num_events),
+                      C.c_int(int(sig_match_thresh is not None)),
+                      f64(0.0 if sig_match_thresh is None else sig_match_thresh),
+                      C.byref(sl), C.byref(epb), C.byref(st)))
+        return st.value, sl.value, epb.value
+
+    def batch_set_read_inputs(self, scale_values=None, stall_ints=None):
+        """scale_values: (n, 5) array with NaN shift where absent, or None;
+        stall_ints: list (per read) of lists of (start, end), or None."""
+        sv = None
+        if scale_values is not None:
+            sv = np.ascontiguousarray(scale_values, dtype=np.float64)
+        flat = off = None
+        if stall_ints is not None:
+            off = np.zeros(len(stall_ints) + 1, dtype=np.int64)
+            off[1:] = np.cumsum([len(s) for s in stall_ints])
+            flat = np.zeros(max(1, int(off[-1])) * 2, dtype=np.int64)
+            k = 0
+            for s in stall_ints:
+                for a, b in s:
+                    flat[2 * k], flat[2 * k + 1] = a, b
+                    k += 1
+        fn = self.lib.tb2_batch_set_read_inputs
+        fn.restype = C.c_int
+        self.check(fn(self.handle, sv.ctypes.data_as(C.c_void_p) if sv is not None else None,
+                      ptr(flat, i64) if flat is not None else None,
+                      ptr(off, i64) if off is not None else None))
+
     # ---- the batched hot path ----------------------------------------------
     def resquiggle_batch(self, raw, raw_off, seq, seq_off, params, save_params,
                          policy, want_norm_signal=False, out=None):

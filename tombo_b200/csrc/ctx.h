@@ -46,7 +46,9 @@ struct tb2_ctx {
     DevBuf model_means, model_sds, alt_means;
     int kmer_width = 0, central_pos = 0, alt_kmer_width = 0;
     // generic scratch pool (named slots), grow-only
-    std::vector<DevBuf> pool = std::vector<DevBuf>(64);
+    // slots: 0-11 mirror calls, 12-49 batch arrays (pipeline.cu), 50-69 llr.cu,
+    // 70-79 per-warp scratch pools
+    std::vector<DevBuf> pool = std::vector<DevBuf>(96);
     // pinned host staging for small results
     void *pinned = nullptr;
     size_t pinned_cap = 0;

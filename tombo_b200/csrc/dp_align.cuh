@@ -170,7 +170,8 @@ __device__ int tb2_emit_segs(const AlignRead &a, const int *cpts, int n_idx)
 }
 
 // find_static_base_assignment resquiggle.py:547-600 + get_short_read_results
-__device__ int tb2_static_assign(const AlignRead &a, const WarpRes &wr, const DpConsts &c)
+__device__ int tb2_static_assign(const AlignRead &a, const WarpRes &wr, const DpConsts &c,
+                                 bool emit_segs = true)
 {
     const int lane = tb2_lane();
     const int n_em = a.n_cpts - 1, nb = a.nb;
@@ -193,6 +194,7 @@ __device__ int tb2_static_assign(const AlignRead &a, const WarpRes &wr, const Dp
     if (st != TB2_OK) return st;
     st = tb2_traceback_dyn(wpl, wr.tb, a.starts, nb, pc.W, pc.chunk, amax, -1, a.read_tb);
     if (st != TB2_OK) return st;
+    if (!emit_segs) return TB2_OK;
     return tb2_emit_segs(a, a.cpts, a.n_cpts);
 }
 

@@ -66,7 +66,7 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
     const int max_useful = (b.n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS;
     if (grid > max_useful) grid = std::max(1, max_useful);
     const size_t slots = (size_t)grid * ALIGN_WARPS;
-    enum { SLOT_TB = 40, SLOT_GROW = 41, SLOT_CNT = 42 };
+    enum { SLOT_TB = 70, SLOT_GROW = 71, SLOT_CNT = 72 };
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_TB].reserve(slots * cfg.tb_words * sizeof(uint32_t)));
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_GROW].reserve(slots * 2 * (size_t)cfg.grow_cells * sizeof(double) + 8));
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT].reserve(sizeof(int)));
@@ -435,4 +435,110 @@ extern "C" int tb2_debug_last_assignment(tb2_ctx *ctx, int64_t n_bases, int64_t 
     for (int64_t i = 0; i < n_bases; ++i) starts_out[i] = h[i];
     for (int64_t i = 0; i <= n_bases; ++i) read_tb_out[i] = h[(n_bases + 1) + i];
     return TB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// single-read mirrors of find_static_base_assignment (resquiggle.py:547-600) and
+// find_seq_start_in_events (resquiggle.py:685-752)
+// ---------------------------------------------------------------------------
+__global__ void k_single(int mode, const double *em, int n_em, const double *rm, const double *rs,
+                         int nb, tb2_params p, int num_bases, int num_events, int check_score,
+                         double sig_match_thresh, int *starts, int *read_tb, uint32_t *tbp,
+                         size_t tb_words, double *grow, int grow_cells, int smem_cells,
+                         int *out_int /* status, start_loc */, double *out_epb)
+{
+    extern __shared__ double smem[];
+    const int lane = tb2_lane();
+    WarpRes wr;
+    wr.smem_rows = smem; wr.smem_cap = smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
+    wr.tb = tbp; wr.tb_words = tb_words;
+    DpConsts c;
+    c.z_shift = p.z_shift; c.stay_pen = p.stay_pen; c.skip_pen = p.skip_pen;
+    c.winsor = !isnan(p.max_half_z_score);
+    c.mhz = c.winsor ? p.max_half_z_score : 0.0;
+    AlignRead a;
+    a.cpts = nullptr; a.n_cpts = n_em + 1; a.em = em; a.rm = rm; a.rs = rs; a.nb = nb;
+    a.starts = starts; a.read_tb = read_tb; a.segs = nullptr; a.rsrtr = nullptr; a.dbg = nullptr;
+    int st, sloc = 0;
+    double epb = 0;
+    if (mode == 0) st = tb2_static_assign(a, wr, c, /*emit_segs=*/false);
+    else st = tb2_start_find(a, wr, c, num_bases, num_events, check_score != 0, sig_match_thresh,
+                             &sloc, &epb);
+    if (lane == 0) { out_int[0] = st; out_int[1] = sloc; *out_epb = epb; }
+}
+
+static int run_single(tb2_ctx *ctx, int mode, const double *em, int64_t n_em, const double *rm,
+                      const double *rs, int64_t nb, const tb2_params *p, int64_t num_bases,
+                      int64_t num_events, int check, double thresh, int64_t *tb_out,
+                      int64_t n_tb_out, int64_t *start_loc, double *epb, int *read_status)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!em || !rm || !rs || !p || n_em < 1 || nb < 1) return TB2_ERR_INVALID_ARG;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    const long long W = mode == 0 ? std::max<long long>(1, n_em - std::min<long long>(nb, n_em) / 4)
+                                  : num_events;
+    const long long rows = mode == 0 ? nb : num_bases;
+    if (W < 1 || rows < 1) return TB2_ERR_INVALID_ARG;
+    if (tb2_row_cells(W) / 32 > TB2_MAX_CHUNK) { if (read_status) *read_status = TB2_ERR_CAPACITY; return TB2_OK; }
+    const DbgGeom g = dbg_geom(W);
+    const size_t tbw = tb2_tb_words(rows, W);
+    TB2_CUDA_TRY(ctx, P[S_A].reserve((size_t)n_em * 8));
+    TB2_CUDA_TRY(ctx, P[S_B].reserve((size_t)nb * 8));
+    TB2_CUDA_TRY(ctx, P[S_C].reserve((size_t)nb * 8));
+    TB2_CUDA_TRY(ctx, P[S_D].reserve((size_t)(nb + 1) * 4 * 2 + 64));
+    TB2_CUDA_TRY(ctx, P[S_E].reserve(tbw * 4 + 64));
+    TB2_CUDA_TRY(ctx, P[S_G].reserve(64));
+    TB2_CUDA_TRY(ctx, P[S_H].reserve((size_t)g.grow_cells * 2 * 8 + 8));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[S_A].p, em, (size_t)n_em * 8, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[S_B].p, rm, (size_t)nb * 8, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[S_C].p, rs, (size_t)nb * 8, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(k_single, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)g.smem_bytes));
+    int *ints = P[S_D].as<int>();
+    k_single<<<1, 32, g.smem_bytes, s>>>(mode, P[S_A].as<double>(), (int)n_em, P[S_B].as<double>(),
+                                         P[S_C].as<double>(), (int)nb, *p, (int)num_bases,
+                                         (int)num_events, check, thresh, ints, ints + (nb + 1),
+                                         P[S_E].as<uint32_t>(), tbw, P[S_H].as<double>(),
+                                         g.grow_cells, g.smem_cells, P[S_G].as<int>(),
+                                         (double *)(P[S_G].as<int>() + 4));
+    TB2_CHECK_LAUNCH(ctx);
+    int small[6];
+    std::vector<int> tb32((size_t)nb + 1);
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(small, P[S_G].p, 24, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(tb32.data(), ints + (nb + 1), (size_t)(nb + 1) * 4, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (read_status) *read_status = small[0];
+    if (small[0] == TB2_OK) {
+        if (tb_out) for (int64_t i = 0; i < n_tb_out; ++i) tb_out[i] = tb32[i];
+        if (start_loc) *start_loc = small[1];
+        if (epb) memcpy(epb, &small[4], 8);
+    }
+    return TB2_OK;
+}
+
+extern "C" int tb2_find_static_base_assignment(tb2_ctx *ctx, const double *event_means,
+                                               int64_t n_events, const double *ref_means,
+                                               const double *ref_sds, int64_t n_bases,
+                                               const tb2_params *params, int64_t *read_tb_out,
+                                               int *read_status)
+{
+    if (!read_tb_out) return TB2_ERR_INVALID_ARG;
+    return run_single(ctx, 0, event_means, n_events, ref_means, ref_sds, n_bases, params, 0, 0, 0,
+                      0.0, read_tb_out, n_bases + 1, nullptr, nullptr, read_status);
+}
+
+extern "C" int tb2_find_seq_start_in_events(tb2_ctx *ctx, const double *event_means,
+                                            int64_t n_events, const double *ref_means,
+                                            const double *ref_sds, int64_t n_ref,
+                                            const tb2_params *params, int64_t num_bases,
+                                            int64_t num_events, int check_score,
+                                            double sig_match_thresh, int64_t *start_loc,
+                                            double *events_per_base, int *read_status)
+{
+    if (!start_loc || !events_per_base || num_bases < 1 || num_events < 1) return TB2_ERR_INVALID_ARG;
+    return run_single(ctx, 1, event_means, n_events, ref_means, ref_sds, n_ref, params, num_bases,
+                      num_events, check_score, sig_match_thresh, nullptr, 0, start_loc,
+                      events_per_base, read_status);
 }

@@ -210,3 +210,90 @@ extern "C" int tb2_new_mean_stds(tb2_ctx *ctx, const double *sig, int64_t n_sig,
     TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return TB2_OK;
 }
+
+// ---------------------------------------------------------------------------
+// batched mirrors of the three Cython scorers over explicit windows:
+// mode 0 c_calc_scaled_llh_ratio_const_var (_c_helper.pyx:313-358)
+// mode 1 c_calc_llh_ratio_const_var (:298-311), mode 2 c_calc_llh_ratio (:277-296)
+// means / ref_means / alt_means: n x K row-major; var_a: const_var[n] (modes 0,1)
+// or ref_vars[n x K] (mode 2); var_b: alt_vars[n x K] (mode 2)
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void k_llh_windows(int mode, long long n, int K, const double *m, const double *rm,
+                              const double *am, const double *va, const double *vb, double sf,
+                              double hf, double hp, double *out)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double *pm = m + s * K, *pr = rm + s * K, *pa = am + s * K;
+    double acc = 0.0;
+    if (mode == 2) {
+        double rz = 0, rl = 0, az = 0, al = 0;
+        for (int i = 0; i < K; ++i) {
+            const double rd = pm[i] - pr[i];
+            rz += (rd * rd) / va[s * K + i];
+            rl += log(va[s * K + i]);
+            const double ad = pm[i] - pa[i];
+            az += (ad * ad) / vb[s * K + i];
+            al += log(vb[s * K + i]);
+        }
+        out[s] = az + al - rz - rl;
+        return;
+    }
+    const double cv = va[s];
+    for (int i = 0; i < K; ++i) {
+        const double obs = pm[i], ref_mean = pr[i], alt_mean = pa[i];
+        if (mode == 1) {
+            const double rd = obs - ref_mean, ad = obs - alt_mean;
+            acc += ((ad * ad) - (rd * rd)) / cv;
+        } else {
+            if (ref_mean == alt_mean) continue;
+            const double scale_mean = (alt_mean + ref_mean) / 2;
+            const double ref_diff = obs - ref_mean, alt_diff = obs - alt_mean;
+            const double scale_diff = obs - scale_mean;
+            double means_diff = alt_mean - ref_mean;
+            if (means_diff < 0) means_diff = means_diff * -1;
+            acc += exp(-(scale_diff * scale_diff) / (sf * cv)) *
+                   ((alt_diff * alt_diff) - (ref_diff * ref_diff)) / (cv * pow(means_diff, hp) * hf);
+        }
+    }
+    out[s] = acc;
+}
+}  // namespace
+
+extern "C" int tb2_calc_llh_ratio_windows(tb2_ctx *ctx, int mode, int64_t n_sites, int kmer_width,
+                                          const double *means, const double *ref_means,
+                                          const double *alt_means, const double *var_a,
+                                          const double *var_b, double scale_factor,
+                                          double height_factor, double height_power,
+                                          double *llr_out)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (mode < 0 || mode > 2 || n_sites < 0 || kmer_width < 1 || !var_a || (mode == 2 && !var_b))
+        return TB2_ERR_INVALID_ARG;
+    if (n_sites == 0) return TB2_OK;
+    if (!means || !ref_means || !alt_means || !llr_out) return TB2_ERR_INVALID_ARG;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    const size_t nk = (size_t)n_sites * kmer_width * 8, nv = (size_t)n_sites * 8;
+    TB2_CUDA_TRY(ctx, P[L_MEAN].reserve(nk));
+    TB2_CUDA_TRY(ctx, P[L_A].reserve(nk));
+    TB2_CUDA_TRY(ctx, P[L_B].reserve(nk));
+    TB2_CUDA_TRY(ctx, P[L_C].reserve(mode == 2 ? nk : nv));
+    TB2_CUDA_TRY(ctx, P[L_D].reserve(mode == 2 ? nk : 8));
+    TB2_CUDA_TRY(ctx, P[L_LLR].reserve(nv));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_MEAN].p, means, nk, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_A].p, ref_means, nk, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_B].p, alt_means, nk, cudaMemcpyHostToDevice, s));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_C].p, var_a, mode == 2 ? nk : nv, cudaMemcpyHostToDevice, s));
+    if (mode == 2) TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_D].p, var_b, nk, cudaMemcpyHostToDevice, s));
+    k_llh_windows<<<(unsigned)((n_sites + 127) / 128), 128, 0, s>>>(
+        mode, n_sites, kmer_width, P[L_MEAN].as<double>(), P[L_A].as<double>(), P[L_B].as<double>(),
+        P[L_C].as<double>(), P[L_D].as<double>(), scale_factor, height_factor, height_power,
+        P[L_LLR].as<double>());
+    TB2_CHECK_LAUNCH(ctx);
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(llr_out, P[L_LLR].p, nv, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return TB2_OK;
+}

@@ -20,8 +20,20 @@ namespace {
 enum {
     B_RAWOFF = 12, B_SEQOFF, B_BASEOFF, B_EVOFF, B_SEQ, B_RAWIN, B_RAWF, B_NORM, B_CS, B_SCORES,
     B_CSTATE, B_CPTS, B_EM, B_RM, B_RS, B_BM, B_TMPB, B_STARTS, B_READTB, B_SEGSDP, B_SEGS,
-    B_STALLS, B_STATE, B_DBG, B_COUNTERS, B_OUT_SEGS, B_OUT_NORMMEAN, B_OUT_NORMSIG, B_OUT_SMALL
+    B_STALLS, B_STATE, B_DBG, B_COUNTERS, B_OUT_SEGS, B_OUT_NORMMEAN, B_OUT_NORMSIG, B_OUT_SMALL,
+    B_SVIN, B_NSTALL
 };
+
+// optional caller-provided per-read inputs of resquiggle_read: map_res.scale_values
+// and map_res.stall_ints (resquiggle.py:1079-1084, 1101-1103)
+__global__ void k_apply_inputs(BatchView b, const tb2_scale_values *sv_in, const int *n_stalls)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= b.n_reads) return;
+    ReadState &s = b.st[r];
+    if (n_stalls) s.n_stalls = n_stalls[r];
+    if (sv_in && s.active && !isnan(sv_in[r].shift)) { s.use_sv = 1; s.sv = sv_in[r]; }
+}
 
 struct HostBatch {
     int n = 0;
@@ -267,6 +279,7 @@ struct BatchHolder {
     std::vector<int64_t> raw_off;
     int raw_dtype = 0;
     bool uploaded = false, computed = false, has_norm_sig = false;
+    bool has_sv_in = false, has_stalls_in = false;
 };
 
 BatchHolder *holder_of(tb2_ctx *ctx)
@@ -302,6 +315,45 @@ extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, 
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_SEQ].p, seq, (size_t)h->hb.total_seq, cudaMemcpyHostToDevice, s));
     TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     h->uploaded = true;
+    h->has_sv_in = h->has_stalls_in = false;
+    return TB2_OK;
+}
+
+extern "C" int tb2_batch_set_read_inputs(tb2_ctx *ctx, const tb2_scale_values *sv_in,
+                                         const int64_t *stall_ints, const int64_t *stall_off)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    BatchHolder *h = holder_of(ctx);
+    if (!h->uploaded) { ctx->err = "tb2_batch_upload has not been called"; return TB2_ERR_INVALID_ARG; }
+    const int n = h->hb.n;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    h->has_sv_in = sv_in != nullptr;
+    if (sv_in) {
+        TB2_CUDA_TRY(ctx, P[B_SVIN].reserve((size_t)n * sizeof(tb2_scale_values)));
+        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_SVIN].p, sv_in, (size_t)n * sizeof(tb2_scale_values), cudaMemcpyHostToDevice, s));
+    }
+    h->has_stalls_in = stall_off != nullptr;
+    if (stall_off) {
+        int cap = 1;
+        for (int r = 0; r < n; ++r) cap = std::max<int>(cap, (int)(stall_off[r + 1] - stall_off[r]));
+        std::vector<int> flat((size_t)n * 2 * cap, 0), cnt((size_t)n, 0);
+        for (int r = 0; r < n; ++r) {
+            cnt[r] = (int)(stall_off[r + 1] - stall_off[r]);
+            for (int k = 0; k < cnt[r]; ++k) {
+                flat[((size_t)r * cap + k) * 2] = (int)stall_ints[2 * (stall_off[r] + k)];
+                flat[((size_t)r * cap + k) * 2 + 1] = (int)stall_ints[2 * (stall_off[r] + k) + 1];
+            }
+        }
+        TB2_CUDA_TRY(ctx, P[B_STALLS].reserve(flat.size() * 4 + 8));
+        TB2_CUDA_TRY(ctx, P[B_NSTALL].reserve((size_t)n * 4));
+        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_STALLS].p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, s));
+        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_NSTALL].p, cnt.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        h->v.stall_ints = P[B_STALLS].as<int>();
+        h->v.stall_cap = cap;
+    }
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return TB2_OK;
 }
 
@@ -332,7 +384,7 @@ extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
     h->has_norm_sig = want_norm_signal != 0;
     double *norm_mean_dev = P[B_OUT_NORMMEAN].as<double>();
     if ((rc = tb2_launch_prep(ctx, v, P[B_RAWIN].p, h->raw_dtype, sp.is_rna, hb.total_s, hb.total_b))) return rc;
-    if (sp.is_rna && (rc = tb2_launch_stalls(ctx, v))) return rc;
+    if (sp.is_rna && !h->has_stalls_in && (rc = tb2_launch_stalls(ctx, v))) return rc;
     const size_t rawdp_cap = (size_t)1 << 15;
     double ms_dp = 0, dp_reads = 0;
     int dp_launches = 0;
@@ -343,6 +395,12 @@ extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
         AlignLaunchCfg acfg;
         plan_align_batch(p, hb, h->raw_off.data(), sp.min_event_to_seq_ratio, &acfg);
         if ((rc = tb2_launch_start_attempt(ctx, v, attempt))) return rc;
+        if (h->has_sv_in || h->has_stalls_in) {
+            k_apply_inputs<<<(n + 255) / 256, 256, 0, s>>>(
+                v, h->has_sv_in ? P[B_SVIN].as<tb2_scale_values>() : nullptr,
+                h->has_stalls_in ? P[B_NSTALL].as<int>() : nullptr);
+            TB2_CHECK_LAUNCH(ctx);
+        }
         double active_now = attempt == 0 ? n : counters[1];
         for (int it = 0; it < std::max(1, sp.max_scaling_iters); ++it) {
             if ((rc = run_call(ctx, v, p, sp, acfg, it == 0, norm_mean_dev, norm_sig_dev, rawdp_cap)))
@@ -657,5 +715,31 @@ extern "C" int tb2_resolve_skipped_bases_with_raw(tb2_ctx *ctx, const int64_t *s
         TB2_CUDA_TRY(ctx, cudaMemcpy(s32.data(), o.v.segs, (size_t)(n_bases + 1) * 4, cudaMemcpyDeviceToHost));
         for (int64_t i = 0; i <= n_bases; ++i) segs_out[i] = s32[i];
     }
+    return TB2_OK;
+}
+
+extern "C" int tb2_identify_stalls(tb2_ctx *ctx, const double *raw, int64_t n, int64_t *ints_out,
+                                   int64_t cap, int64_t *n_out)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!raw || !ints_out || !n_out || n < 1 || cap < 1) return TB2_ERR_INVALID_ARG;
+    OneRead o;
+    if ((rc = one_read_view(ctx, o, raw, n, 1, default_params(), 2))) return rc;
+    auto &P = ctx->pool;
+    const int scap = 4096;
+    TB2_CUDA_TRY(ctx, P[B_STALLS].reserve((size_t)2 * scap * 4));
+    o.v.stall_ints = P[B_STALLS].as<int>();
+    o.v.stall_cap = scap;
+    if ((rc = tb2_launch_stalls(ctx, o.v))) return rc;
+    ReadState st;
+    if ((rc = fetch_state(ctx, o.v, &st))) return rc;
+    if (st.status != TB2_OK) return st.status;
+    if (st.n_stalls > cap) return TB2_ERR_CAPACITY;
+    std::vector<int> h((size_t)2 * std::max(1, st.n_stalls));
+    if (st.n_stalls > 0)
+        TB2_CUDA_TRY(ctx, cudaMemcpy(h.data(), o.v.stall_ints, (size_t)2 * st.n_stalls * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 2 * st.n_stalls; ++i) ints_out[i] = h[i];
+    *n_out = st.n_stalls;
     return TB2_OK;
 }

@@ -993,7 +993,7 @@ int tb2_launch_stalls(tb2_ctx *ctx, const BatchView &b)
 int tb2_launch_resolve(tb2_ctx *ctx, const BatchView &b, const tb2_params &p,
                        const StagePolicy &pol, size_t cap)
 {
-    enum { SLOT_RAWDP = 43, SLOT_CNT2 = 44 };
+    enum { SLOT_RAWDP = 73, SLOT_CNT2 = 74 };
     const int warps_per_block = 4;
     int grid = ctx->sm_count * 8;
     const int max_useful = (b.n_reads + warps_per_block - 1) / warps_per_block;

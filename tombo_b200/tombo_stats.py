@@ -1,0 +1,371 @@
+"""``tombo.tombo_stats`` surface of the resquiggle hot path, bound to the CUDA
+library: k-mer models, signal normalisation, base means, sequence based rescaling,
+parameter loading and per-read alternative-model log-likelihood ratios
+(tombo_stats.py:203-573, 580-1123, 1505-1597, 2327-2370, 3888-4082).
+
+Everything numeric runs in CUDA kernels through the C ABI (include/tombo_b200.h);
+what the reference itself does in plain Python (parameter tuples, dict look-ups,
+regex motif search, a two-line numpy score) stays plain Python here."""
+import numpy as np
+
+from . import _lib
+from . import tombo_helper as th
+from ._default_parameters import (
+    ALGN_PARAMS_TABLE, SEG_PARAMS_TABLE, RNA_SAMP_TYPE, DNA_SAMP_TYPE,
+    MIN_EVENT_TO_SEQ_RATIO, OCLLHR_SCALE, OCLLHR_HEIGHT, OCLLHR_POWER, STALL_PARAMS)
+
+__all__ = [
+    'TomboModel', 'AltModel', 'normalize_raw_signal', 'compute_base_means',
+    'get_read_seg_score', 'calc_kmer_fitted_shift_scale', 'load_resquiggle_parameters',
+    'compute_num_events', 'get_dynamic_prog_params', 'identify_stalls',
+    'compute_alt_model_read_stats', 'trim_seq_and_means']
+
+# E|N(0,1)| = sqrt(2 / pi); the reference evaluates scipy.stats.halfnorm.expect()
+# (tombo_stats.py:84), which returns this value
+HALF_NORM_EXPECTED_VAL = float(np.sqrt(2.0 / np.pi))
+STANDARD_MODEL_NAME = 'standard'
+CONST_SD_MODEL = True                     # tombo_stats.py:112
+NORM_TYPES = ('none', 'pA', 'pA_raw', 'median', 'robust_median', 'median_const_scale')
+_CODE = {'A': 0, 'C': 1, 'G': 2, 'T': 3}
+
+
+def _kmer_code(kmer):
+    idx = 0
+    for b in kmer:
+        idx = idx * 4 + _CODE[b]
+    return idx
+
+
+class TomboModel(object):
+    """Canonical k-mer model (tombo_stats.py:580-919).  Built from ``kmer_ref`` (a
+    list of ``(kmer, mean, sd)``) and ``central_pos``; model files need h5py and
+    are outside the hot path."""
+
+    def __init__(self, ref_fn=None, is_text_model=False, kmer_ref=None, central_pos=None,
+                 seq_samp_type=None, reads_index=None, fast5_fns=None, minimal_startup=True):
+        if kmer_ref is None:
+            raise th.TomboError(
+                'tombo_b200.TomboModel is initialised from kmer_ref=/central_pos= '
+                '(model files are read by the reference with h5py)')
+        assert central_pos is not None, (
+            'central_pos must be provided is TomboModel is loaded with a kmer_ref')
+        self.means, self.sds = {}, {}
+        for kmer, kmer_mean, kmer_std in kmer_ref:
+            try:
+                kmer = kmer.decode()
+            except AttributeError:
+                pass
+            self.means[kmer] = kmer_mean
+            self.sds[kmer] = kmer_std
+        self.central_pos = central_pos
+        self.name = STANDARD_MODEL_NAME
+        self.seq_samp_type = seq_samp_type
+        self.kmer_width = len(next(k for k in self.means))
+        self.inv_var = None
+        if not minimal_startup:
+            self.inv_var = dict((k, 1 / (s * s)) for k, s in self.sds.items())
+        self._tables = None
+
+    def tables(self):
+        """dense (means, sds) indexed by the base-4 k-mer code (device layout)"""
+        if self._tables is None:
+            n = 4 ** self.kmer_width
+            m, s = np.full(n, np.nan), np.full(n, np.nan)
+            for k, v in self.means.items():
+                if all(b in _CODE for b in k):
+                    m[_kmer_code(k)] = v
+                    s[_kmer_code(k)] = self.sds[k]
+            self._tables = (m, s)
+        return self._tables
+
+    def reverse_sequence_copy(self):
+        rev = TomboModel(kmer_ref=[(k[::-1], m, self.sds[k]) for k, m in self.means.items()],
+                         central_pos=self.kmer_width - self.central_pos - 1,
+                         seq_samp_type=self.seq_samp_type,
+                         minimal_startup=self.inv_var is None)
+        return rev
+
+    def get_exp_levels_from_seq(self, seq, rev_strand=False):
+        """tombo_stats.py:834-862"""
+        seq_kmers = th.get_seq_kmers(seq, self.kmer_width, rev_strand)
+        return self.get_exp_levels_from_kmers(seq_kmers)
+
+    def get_exp_levels_from_kmers(self, seq_kmers):
+        """tombo_stats.py:864-884"""
+        try:
+            ref_means = np.array([self.means[kmer] for kmer in seq_kmers])
+            ref_sds = np.array([self.sds[kmer] for kmer in seq_kmers])
+        except KeyError:
+            raise th.TomboError('Invalid sequence encountered from genome sequence.')
+        return ref_means, ref_sds
+
+
+class AltModel(object):
+    """Alternative-base k-mer model (tombo_stats.py:922-1123), from ``kmer_ref`` rows
+    ``(kmer, pos, mean, sd)``."""
+
+    def __init__(self, ref_fn=None, kmer_ref=None, central_pos=None, alt_base=None, name=None,
+                 motif=None, minimal_startup=True):
+        if kmer_ref is None:
+            raise th.TomboError('tombo_b200.AltModel is initialised from kmer_ref=')
+        assert central_pos is not None and alt_base is not None, (
+            'central_pos and alt_base must be provided if AltModel is loaded with a kmer_ref')
+        self.means, self.sds = {}, {}
+        for kmer, pos, kmer_mean, kmer_std in kmer_ref:
+            try:
+                kmer = kmer.decode()
+            except AttributeError:
+                pass
+            self.means[(kmer, pos)] = kmer_mean
+            self.sds[(kmer, pos)] = kmer_std
+        self.central_pos = central_pos
+        self.alt_base = alt_base
+        self.name = name
+        if motif is None:
+            self.motif = th.TomboMotif(self.alt_base, 1)
+        else:
+            assert isinstance(motif, th.TomboMotif) and motif.mod_pos is not None
+            self.motif = motif
+        self.kmer_width = len(next(kmer for kmer, pos in self.means))
+        self.inv_var = None
+        self._table = None
+
+    def table(self):
+        """dense alt means [code, pos] (NaN where absent) -- the device layout"""
+        if self._table is None:
+            t = np.full((4 ** self.kmer_width, self.kmer_width), np.nan)
+            for (k, pos), v in self.means.items():
+                t[_kmer_code(k), pos] = v
+            self._table = t
+        return self._table
+
+    def get_exp_level(self, kmer, pos):
+        return self.means.get((kmer, pos), np.nan)
+
+    def get_exp_sd(self, kmer, pos):
+        return self.sds.get((kmer, pos), np.nan)
+
+    def get_exp_levels_from_kmers(self, seq_kmers, rev_strand=False):
+        """tombo_stats.py:1096-1123"""
+        pos_range = (range(self.kmer_width) if rev_strand
+                     else range(self.kmer_width - 1, -1, -1))
+        ref_means = np.array([self.get_exp_level(k, p) for k, p in zip(seq_kmers, pos_range)])
+        ref_sds = np.array([self.get_exp_sd(k, p) for k, p in zip(seq_kmers, pos_range)])
+        return ref_means, ref_sds
+
+
+# ---------------------------------------------------------------------------
+# signal normalisation (tombo_stats.py:203-233, 482-573)
+# ---------------------------------------------------------------------------
+def compute_base_means(all_raw_signal, base_starts):
+    """c_new_means over ``base_starts`` (tombo_stats.py:203-215)"""
+    return _lib.get_context().new_means(
+        np.asarray(all_raw_signal).astype(np.float64), base_starts)
+
+
+def normalize_raw_signal(
+        all_raw_signal, read_start_rel_to_raw=0, read_obs_len=None, norm_type='median',
+        outlier_thresh=None, channel_info=None, scale_values=None, event_means=None,
+        model_means=None, model_inv_vars=None, const_scale=None):
+    """tombo_stats.py:482-573 for the normalisation types the resquiggle path uses:
+    ``median``, ``median_const_scale`` and provided ``scale_values``."""
+    if read_obs_len is None:
+        read_obs_len = all_raw_signal.shape[0] - read_start_rel_to_raw
+    if norm_type not in NORM_TYPES and scale_values is None:
+        raise th.TomboError(
+            'Normalization type ' + norm_type + ' is not a valid option and shift or scale '
+            'parameters were not provided.')
+    raw_signal = all_raw_signal[read_start_rel_to_raw:read_start_rel_to_raw + read_obs_len]
+    if scale_values is None and norm_type not in ('median', 'median_const_scale'):
+        raise NotImplementedError(
+            'norm_type ' + norm_type + ' is not on the resquiggle path (SURVEY.md 8a)')
+    if scale_values is None and norm_type == 'median_const_scale':
+        assert const_scale is not None
+    st, norm, sv = _lib.get_context().normalize_raw_signal(
+        np.asarray(raw_signal, dtype=np.float64), outlier_thresh=outlier_thresh,
+        scale_values=scale_values,
+        const_scale=const_scale if (scale_values is None and
+                                    norm_type == 'median_const_scale') else None)
+    if st == 100:
+        raise FloatingPointError('divide by zero encountered in signal normalization')
+    th._raise_status(st)
+    none = lambda v: None if np.isnan(v) else v   # noqa: E731
+    return norm, th.scaleValues(sv[0], sv[1], none(sv[2]), none(sv[3]), outlier_thresh)
+
+
+def identify_stalls(all_raw_signal, stall_params=None, return_metric=False):
+    """Mean-window stall detection (tombo_stats.py:269-368 with MEAN_STALL_PARAMS)."""
+    if return_metric:
+        raise NotImplementedError('return_metric is a plotting debug aid of the reference')
+    if stall_params is not None:
+        d = dict(STALL_PARAMS)
+        given = dict((k, getattr(stall_params, k)) for k in d)
+        if given != d:
+            raise NotImplementedError('only the default mean-window stall parameters')
+    ints = _lib.get_context().identify_stalls(np.asarray(all_raw_signal, dtype=np.float64))
+    return [list(map(int, iv)) for iv in ints]
+
+
+def calc_kmer_fitted_shift_scale(
+        prev_shift, prev_scale, r_event_means, r_model_means, r_model_inv_vars=None,
+        method='theil_sen', subsample_key=0):
+    """Theil-Sen sequence based rescaling (tombo_stats.py:370-450).  Reads with more
+    than MAX_POINTS_FOR_THEIL_SEN bases are sub-sampled with a keyed bijection
+    (``subsample_key``) instead of the reference's unseeded np.random.choice."""
+    if method != 'theil_sen':
+        raise NotImplementedError('only method="theil_sen" is on the resquiggle path')
+    st, out = _lib.get_context().theil_sen(
+        prev_shift, prev_scale, r_event_means, r_model_means, subsample_key)
+    th._raise_status(st)
+    return out
+
+
+def get_read_seg_score(r_means, r_ref_means, r_ref_sds):
+    """tombo_stats.py:2327-2338 (a numpy one-liner in the reference too)"""
+    return np.mean(np.abs((r_means - r_ref_means) / r_ref_sds))
+
+
+def get_dynamic_prog_params(match_evalue):
+    """tombo_stats.py:2364-2370"""
+    return HALF_NORM_EXPECTED_VAL + match_evalue, match_evalue
+
+
+def load_resquiggle_parameters(seq_samp_type, sig_aln_params=None, seg_params=None,
+                               use_save_bandwidth=False):
+    """tombo_stats.py:1505-1556"""
+    if sig_aln_params is None:
+        (match_evalue, skip_pen, bandwidth, save_bandwidth, max_half_z_score, band_bound_thresh,
+         start_bw, start_save_bw, start_n_bases) = ALGN_PARAMS_TABLE[seq_samp_type.name]
+    else:
+        (match_evalue, skip_pen, bandwidth, save_bandwidth, max_half_z_score, band_bound_thresh,
+         start_bw, start_save_bw, start_n_bases) = sig_aln_params
+        bandwidth, save_bandwidth = int(bandwidth), int(save_bandwidth)
+        band_bound_thresh, start_bw = int(band_bound_thresh), int(start_bw)
+        start_save_bw, start_n_bases = int(start_save_bw), int(start_n_bases)
+    if use_save_bandwidth:
+        bandwidth = save_bandwidth
+    if seg_params is None:
+        (running_stat_width, min_obs_per_base, raw_min_obs_per_base,
+         mean_obs_per_event) = SEG_PARAMS_TABLE[seq_samp_type.name]
+    else:
+        (running_stat_width, min_obs_per_base, raw_min_obs_per_base,
+         mean_obs_per_event) = seg_params
+    z_shift, stay_pen = get_dynamic_prog_params(match_evalue)
+    return th.resquiggleParams(
+        match_evalue, skip_pen, bandwidth, max_half_z_score, running_stat_width,
+        min_obs_per_base, raw_min_obs_per_base, mean_obs_per_event, z_shift, stay_pen,
+        seq_samp_type.name == RNA_SAMP_TYPE, band_bound_thresh, start_bw, start_save_bw,
+        start_n_bases)
+
+
+def compute_num_events(signal_len, seq_len, mean_obs_per_event,
+                       min_event_to_seq_ratio=MIN_EVENT_TO_SEQ_RATIO):
+    """tombo_stats.py:1558-1574"""
+    return max(signal_len // mean_obs_per_event, int(seq_len * min_event_to_seq_ratio))
+
+
+# ---------------------------------------------------------------------------
+# per-read alternative-model statistics (tombo_stats.py:3888-4082)
+# ---------------------------------------------------------------------------
+def trim_seq_and_means(seq, means, r_start, reg_start, reg_end, strand, kmer_width,
+                       central_pos, max_motif_bb, max_motif_ab):
+    """tombo_stats.py:3888-3970"""
+    r_end = r_start + means.shape[0]
+    motif_search_seq = seq
+    num_start_clip, num_end_clip = 0, 0
+    if r_start + kmer_width - 1 < reg_start:
+        if strand == '+':
+            num_start_clip = reg_start - (r_start + kmer_width - 1)
+        else:
+            num_end_clip = reg_start - (r_start + kmer_width - 1)
+        r_start = reg_start - (kmer_width - 1)
+    if r_end - kmer_width + 1 > reg_end:
+        if strand == '+':
+            num_end_clip = r_end - kmer_width + 1 - reg_end
+        else:
+            num_start_clip = r_end - kmer_width + 1 - reg_end
+    seq = seq[num_start_clip:]
+    if num_end_clip > 0:
+        seq = seq[:-num_end_clip]
+    means = means[num_start_clip + central_pos:]
+    means = means[:-(num_end_clip + kmer_width - central_pos - 1)]
+    if means.shape[0] < kmer_width:
+        raise th.TomboError('Read sequence too short in this region.')
+    kmers = th.get_seq_kmers(seq, kmer_width)
+    if len(kmers) != means.shape[0]:
+        raise th.TomboError('Mismatching k-mer and mean levels.')
+    r_start += kmer_width - 1
+    if num_start_clip + kmer_width - 1 - max_motif_bb >= 0:
+        motif_search_seq = motif_search_seq[num_start_clip + kmer_width - 1 - max_motif_bb:]
+    else:
+        motif_search_seq = 'N' * -(
+            num_start_clip + kmer_width - 1 - max_motif_bb) + motif_search_seq
+    if num_end_clip + kmer_width - 1 - max_motif_ab >= 0:
+        motif_search_seq = motif_search_seq[:-(num_end_clip + kmer_width - 1 - max_motif_ab)]
+    else:
+        motif_search_seq = motif_search_seq + 'N' * -(
+            num_end_clip + kmer_width - 1 - max_motif_ab)
+    return kmers, means, r_start, motif_search_seq
+
+
+def compute_alt_model_read_stats(r_data, std_ref, alt_refs, use_standard_llhr=False,
+                                 reg_data=None):
+    """tombo_stats.py:3972-4082.  Read data arrive through
+    ``tombo_helper.get_multiple_slots_read_centric`` / ``get_raw_read_slot`` (the
+    FAST5 seam, :4013-4016); every site's k-mer window is scored on the GPU."""
+    reg_start = reg_data.start if reg_data is not None else r_data.start
+    reg_end = reg_data.end if reg_data is not None else r_data.end
+    max_motif_bb = max([alt_ref.motif.mod_pos - 1 for _, alt_ref in alt_refs])
+    max_motif_ab = max([alt_ref.motif.motif_len - alt_ref.motif.mod_pos
+                        for _, alt_ref in alt_refs])
+    r_means, r_seq = th.get_multiple_slots_read_centric(
+        r_data, ['norm_mean', 'base'], r_data.corr_group)
+    try:
+        read_id = th.get_raw_read_slot(r_data).attrs.get('read_id')
+    except Exception:
+        read_id = getattr(r_data, 'read_id', None)
+    if r_means is None or r_seq is None:
+        raise th.TomboError('Read does not contain valid re-squiggled data.')
+    r_seq = b''.join(r_seq).decode() if not isinstance(r_seq, str) else r_seq
+    r_kmers, r_means, r_start, motif_search_seq = trim_seq_and_means(
+        r_seq, np.asarray(r_means, dtype=np.float64), r_data.start, reg_start, reg_end,
+        r_data.strand, std_ref.kmer_width, std_ref.central_pos, max_motif_bb, max_motif_ab)
+    K = std_ref.kmer_width
+    testable_len = r_means.shape[0] - K + 1
+    r_ref_means, r_ref_sds = std_ref.get_exp_levels_from_kmers(r_kmers)
+    r_ref_vars = np.square(r_ref_sds)
+    ctx = _lib.get_context()
+    all_poss, all_llhrs = {}, {}
+    win = np.arange(K)
+    for alt_name, alt_ref in alt_refs:
+        search = motif_search_seq[max_motif_bb - (alt_ref.motif.mod_pos - 1):]
+        trim_end = max_motif_ab - (alt_ref.motif.motif_len - alt_ref.motif.mod_pos)
+        if trim_end > 0:
+            search = search[:-trim_end]
+        alt_poss = np.array([m.start() for m in alt_ref.motif.motif_pat.finditer(search)],
+                            dtype=np.int64)
+        if r_data.strand == '+':
+            gen_poss = r_start + alt_poss
+        else:
+            gen_poss = r_start + testable_len - alt_poss - 1
+        if alt_poss.shape[0] == 0:
+            all_llhrs[alt_name], all_poss[alt_name] = np.array([]), np.array([])
+            continue
+        idx = alt_poss[:, None] + win[None, :]
+        means_w = r_means[idx]
+        ref_w = r_ref_means[idx]
+        alt_w = np.array([alt_ref.get_exp_levels_from_kmers(r_kmers[p:p + K])[0]
+                          for p in alt_poss])
+        if CONST_SD_MODEL:
+            mode = 1 if use_standard_llhr else 0
+            llhrs = ctx.calc_llh_ratio_windows(mode, means_w, ref_w, alt_w, r_ref_vars[alt_poss],
+                                               None, OCLLHR_SCALE, OCLLHR_HEIGHT, OCLLHR_POWER)
+        else:
+            if not use_standard_llhr:
+                raise th.TomboError('Variable SD scaled likelihood ratio not implemented.')
+            alt_v = np.array([np.square(alt_ref.get_exp_levels_from_kmers(
+                r_kmers[p:p + K])[1]) for p in alt_poss])
+            llhrs = ctx.calc_llh_ratio_windows(2, means_w, ref_w, alt_w, r_ref_vars[idx], alt_v)
+        all_llhrs[alt_name] = llhrs
+        all_poss[alt_name] = gen_poss
+    return all_llhrs, all_poss, read_id
