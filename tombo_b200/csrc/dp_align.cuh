@@ -3,18 +3,21 @@
 // with find_seq_start_in_events (:685-752), _get_masked_start_fwd_pass (:607-683),
 // find_static_base_assignment (:547-600), c_adaptive_banded_forward_pass,
 // c_banded_traceback, _trim_traceback (:754-764), get_rel_raw_coords (:858-864).
+//
+// Static bands (short reads, start search, masked start) run on the wavefront
+// engine, adaptive rows on the lane-chunk engine (dp_row.cuh).
 #pragma once
 #include "dp_row.cuh"
 
-// packed-move words per lane are instantiated for {1,2,3,4,5,8,16}: band widths up
-// to 16*16*32 = 8192 cells
+// packed-move words per lane (lane-chunk layout) are instantiated for
+// {1,2,3,4,5,8,16}: band widths up to 16*16*32 = 8192 cells
 #define TB2_MAX_WPL 16
 #define TB2_MASK_FILL_Z_SCORE (-15.0)
 
 // per-warp resources
 struct WarpRes {
-    double *smem_rows;    // 2 * smem_cap doubles
-    int smem_cap;         // cells per row buffer available in shared memory
+    double *smem_rows;    // smem_cap doubles of shared memory
+    int smem_cap;
     double *grow;         // optional global row scratch, 2 * grow_cap doubles
     int grow_cap;
     uint32_t *tb;         // packed move scratch
@@ -35,14 +38,15 @@ struct AlignRead {
     int *dbg;             // out (may be null): path, mapped_start, clip
 };
 
+// two lane-transposed row buffers for the lane-chunk engine
 __device__ __forceinline__ bool tb2_setup_geom(PassCtx &pc, const WarpRes &wr, int W)
 {
     pc.W = W;
     pc.chunk = (W + 31) / 32;
     const int cells = pc.chunk * 32;
-    if (cells <= wr.smem_cap) {
+    if (2 * cells <= wr.smem_cap) {
         pc.buf0 = wr.smem_rows;
-        pc.buf1 = wr.smem_rows + wr.smem_cap;
+        pc.buf1 = wr.smem_rows + cells;
         return true;
     }
     if (wr.grow != nullptr && cells <= wr.grow_cap) {
@@ -51,6 +55,14 @@ __device__ __forceinline__ bool tb2_setup_geom(PassCtx &pc, const WarpRes &wr, i
         return true;
     }
     return false;
+}
+
+// one plain row buffer (W doubles) for the wavefront engine
+__device__ __forceinline__ double *tb2_wf_rowbuf(const WarpRes &wr, int W)
+{
+    if (W <= wr.smem_cap) return wr.smem_rows;
+    if (wr.grow != nullptr && W <= 2 * wr.grow_cap) return wr.grow;
+    return nullptr;
 }
 
 __device__ __forceinline__ int tb2_wpl_of(int chunk)
@@ -74,17 +86,18 @@ __device__ int tb2_run_rows_dyn(int wpl, const PassCtx &pc, const DpConsts &c, i
     }
 }
 
-__device__ int tb2_traceback_dyn(int wpl, const uint32_t *tb, const int *starts, int nb, int W,
-                                 int chunk, int band_pos, int thresh, int *read_tb)
+__device__ int tb2_tb_seg_chunk_dyn(int wpl, const uint32_t *tb, const int *starts, int row_hi,
+                                    int row_lo, int W, int chunk, int thresh, int *cur_event,
+                                    int *read_tb)
 {
     switch (wpl) {
-    case 1: return tb2_traceback<1>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
-    case 2: return tb2_traceback<2>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
-    case 3: return tb2_traceback<3>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
-    case 4: return tb2_traceback<4>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
-    case 5: return tb2_traceback<5>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
-    case 8: return tb2_traceback<8>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
-    case 16: return tb2_traceback<16>(tb, starts, nb, W, chunk, band_pos, thresh, read_tb);
+    case 1: return tb2_tb_seg_chunk<1>(tb, starts, row_hi, row_lo, W, chunk, thresh, cur_event, read_tb);
+    case 2: return tb2_tb_seg_chunk<2>(tb, starts, row_hi, row_lo, W, chunk, thresh, cur_event, read_tb);
+    case 3: return tb2_tb_seg_chunk<3>(tb, starts, row_hi, row_lo, W, chunk, thresh, cur_event, read_tb);
+    case 4: return tb2_tb_seg_chunk<4>(tb, starts, row_hi, row_lo, W, chunk, thresh, cur_event, read_tb);
+    case 5: return tb2_tb_seg_chunk<5>(tb, starts, row_hi, row_lo, W, chunk, thresh, cur_event, read_tb);
+    case 8: return tb2_tb_seg_chunk<8>(tb, starts, row_hi, row_lo, W, chunk, thresh, cur_event, read_tb);
+    case 16: return tb2_tb_seg_chunk<16>(tb, starts, row_hi, row_lo, W, chunk, thresh, cur_event, read_tb);
     default: return TB2_ERR_CAPACITY;
     }
 }
@@ -98,6 +111,24 @@ __device__ __forceinline__ void tb2_pc_defaults(PassCtx &pc, const AlignRead &a,
     pc.mask_fill = TB2_MASK_FILL_Z_SCORE;
     pc.mask_shifted = (TB2_MASK_FILL_Z_SCORE - c.z_shift) + c.z_shift;  // resquiggle.py:666,678
     pc.starts = a.starts; pc.tb = wr.tb; pc.dbg_fwd = nullptr; pc.dbg_tb = nullptr;
+    pc.buf0 = nullptr; pc.buf1 = nullptr; pc.chunk = 0; pc.W = 0;
+}
+
+// static-band forward pass + traceback over rows [0, n_rows) (wavefront engine)
+__device__ int tb2_static_pass(PassCtx &pc, const WarpRes &wr, const DpConsts &c, int W,
+                               int n_rows, int *read_tb)
+{
+    pc.W = W;
+    double *rowbuf = tb2_wf_rowbuf(wr, W);
+    if (rowbuf == nullptr) return TB2_ERR_CAPACITY;
+    const int wpr = tb2_wf_wpr(W);
+    if ((size_t)n_rows * wpr > wr.tb_words) return TB2_ERR_CAPACITY;
+    int amax = 0;
+    int st = tb2_wavefront_rows(pc, c, TB2_MODE_PLAIN, n_rows, rowbuf, wr.tb, &amax);
+    if (st != TB2_OK) return st;
+    int cur_event = amax + pc.starts[n_rows - 1];
+    if (tb2_lane() == 0) read_tb[n_rows] = cur_event + 1;
+    return tb2_tb_seg_wf(wr.tb, wpr, pc.starts, n_rows, 0, W, -1, &cur_event, read_tb);
 }
 
 // find_seq_start_in_events resquiggle.py:685-752
@@ -111,18 +142,13 @@ __device__ int tb2_start_find(const AlignRead &a, const WarpRes &wr, const DpCon
     if (a.nb < num_bases) return TB2_ERR_MAP_TOO_SHORT_START;
     PassCtx pc;
     tb2_pc_defaults(pc, a, wr, c);
-    if (!tb2_setup_geom(pc, wr, num_events)) return TB2_ERR_CAPACITY;
-    const int wpl = tb2_wpl_of(pc.chunk);
-    if (wpl > TB2_MAX_WPL || (size_t)num_bases * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
-    if (num_bases + 1 > pc.chunk * 32) return TB2_ERR_CAPACITY;  // scoring scratch
     for (int r = lane; r < num_bases; r += 32) a.starts[r] = r;  // :721
     __syncwarp();
-    int sel, amax = 0;
-    tb2_init_row0(pc, &sel);
-    int st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_PLAIN, 0, num_bases, num_bases, &sel, &amax);
+    int st = tb2_static_pass(pc, wr, c, num_events, num_bases, a.read_tb);
     if (st != TB2_OK) return st;
-    st = tb2_traceback_dyn(wpl, wr.tb, a.starts, num_bases, pc.W, pc.chunk, amax, -1, a.read_tb);
-    if (st != TB2_OK) return st;
+    // scoring scratch: the (now free) row buffer
+    double *t = tb2_wf_rowbuf(wr, num_events);
+    if (num_bases + 1 > num_events) return TB2_ERR_CAPACITY;
     int sloc = 0;
     double e = 0;
     if (lane == 0) {
@@ -130,7 +156,6 @@ __device__ int tb2_start_find(const AlignRead &a, const WarpRes &wr, const DpCon
         e = (double)(a.read_tb[num_bases] - a.read_tb[0]) / (double)(num_bases + 1);  // :749
         if (check_score) {
             // score_valid_bases tombo_stats.py:2340-2362 (np.mean = pairwise sum / n)
-            double *t = pc.buf0;
             int nv = 0;
             for (int i = 0; i < num_bases; ++i) {
                 const int s0 = a.read_tb[i], s1 = a.read_tb[i + 1];
@@ -180,19 +205,12 @@ __device__ int tb2_static_assign(const AlignRead &a, const WarpRes &wr, const Dp
     if (W <= 0 || nb <= 0) return TB2_ERR_UNEXPECTED;
     PassCtx pc;
     tb2_pc_defaults(pc, a, wr, c);
-    if (!tb2_setup_geom(pc, wr, W)) return TB2_ERR_CAPACITY;
-    const int wpl = tb2_wpl_of(pc.chunk);
-    if (wpl > TB2_MAX_WPL || (size_t)nb * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
     const int n0 = nb - 2 * mask_len;
     for (int r = lane; r < nb; r += 32)   // :567-569
         a.starts[r] = (r < n0) ? 0
                                : (int)tb2_linspace_at(0.0, (double)mask_len, 2 * mask_len, r - n0);
     __syncwarp();
-    int sel, amax = 0;
-    tb2_init_row0(pc, &sel);
-    int st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_PLAIN, 0, nb, nb, &sel, &amax);
-    if (st != TB2_OK) return st;
-    st = tb2_traceback_dyn(wpl, wr.tb, a.starts, nb, pc.W, pc.chunk, amax, -1, a.read_tb);
+    int st = tb2_static_pass(pc, wr, c, W, nb, a.read_tb);
     if (st != TB2_OK) return st;
     if (!emit_segs) return TB2_OK;
     return tb2_emit_segs(a, a.cpts, a.n_cpts);
@@ -232,7 +250,7 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
         return tb2_static_assign(a, wr, c);
     if (a.dbg && lane == 0) a.dbg[0] = 1;
 
-    // ---- _get_masked_start_fwd_pass :607-683 ----
+    // ---- _get_masked_start_fwd_pass :607-683 (static rows: wavefront engine) ----
     const int n_emc = n_em - clip;
     if (n_emc - mso < bw) return TB2_ERR_START_TOO_FAR;
     PassCtx pc;
@@ -240,7 +258,8 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     pc.em = a.em + clip; pc.n_em = n_emc; pc.mso = mso;
     if (!tb2_setup_geom(pc, wr, bw)) return TB2_ERR_CAPACITY;
     const int wpl = tb2_wpl_of(pc.chunk);
-    if (wpl > TB2_MAX_WPL || (size_t)nb * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
+    const int wpr = tb2_wf_wpr(bw);
+    if (wpl > TB2_MAX_WPL) return TB2_ERR_CAPACITY;
     const int bes0 = (half_bw <= mso) ? 0 : mso - half_bw;
     const int t2 = (int)((double)(half_bw + 1) / epb);
     const int tmp_len = max(max(half_bw, TB2_MASK_BASES), t2) + 1;
@@ -259,6 +278,11 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     int mask_seq_len = max(TB2_MASK_BASES, first + 2);
     if (mask_seq_len > tmp_len) mask_seq_len = tmp_len;
     if (mask_seq_len > nb) return TB2_ERR_UNEXPECTED;
+    // move scratch: wavefront rows first, then the lane-chunk rows (indexed by row)
+    const size_t wf_words = (size_t)mask_seq_len * wpr;
+    if (wf_words + (size_t)nb * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
+    uint32_t *tb_wf = wr.tb, *tb_chunk = wr.tb + wf_words;
+    pc.tb = tb_chunk;
     pc.msp_start = (double)(mso + 1);
     pc.msp_stop = (double)(a.starts[TB2_MASK_BASES - 1] + bw);
     // validate every masked row (the reference raises from inside the loop)
@@ -277,15 +301,28 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
         if (aa < 0 || eml < 0 || sml + nv + eml != bw) bad = 1;
     }
     if (__any_sync(TB2_FULL_MASK, bad)) return TB2_ERR_MASKED_TOO_FEW;
-    int sel, amax = 0;
-    tb2_init_row0(pc, &sel);
-    st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_MASKED, 0, mask_seq_len, nb, &sel, &amax);
+    // the wavefront row buffer is the first half of the two lane-chunk buffers
+    double *rowbuf = pc.buf0;
+    int amax = 0;
+    st = tb2_wavefront_rows(pc, c, TB2_MODE_MASKED, mask_seq_len, rowbuf, tb_wf, &amax);
     if (st != TB2_OK) return st;
-    // ---- adaptive rows :314-412 ----
+    // last masked row -> lane-transposed buffer 1 (source and destination disjoint)
+    for (int j = lane; j < bw; j += 32) {
+        const int lj = j / pc.chunk;
+        pc.buf1[(j - lj * pc.chunk) * 32 + lj] = rowbuf[j];
+    }
+    __syncwarp();
+    int sel = 1;
+    // ---- adaptive rows :314-412 (lane-chunk engine) ----
     st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_ADAPTIVE, mask_seq_len, nb, nb, &sel, &amax);
     if (st != TB2_OK) return st;
-    st = tb2_traceback_dyn(wpl, wr.tb, a.starts, nb, pc.W, pc.chunk, amax,
-                           (int)p.band_bound_thresh, a.read_tb);
+    int cur_event = amax + a.starts[nb - 1];
+    if (lane == 0) a.read_tb[nb] = cur_event + 1;
+    const int thresh = (int)p.band_bound_thresh;
+    st = tb2_tb_seg_chunk_dyn(wpl, tb_chunk, a.starts, nb, mask_seq_len, bw, pc.chunk, thresh,
+                              &cur_event, a.read_tb);
+    if (st != TB2_OK) return st;
+    st = tb2_tb_seg_wf(tb_wf, wpr, a.starts, mask_seq_len, 0, bw, thresh, &cur_event, a.read_tb);
     if (st != TB2_OK) return st;
     // _trim_traceback :754-764
     if (lane == 0) {

@@ -16,7 +16,7 @@ k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, 
     const size_t slot = (size_t)blockIdx.x * ALIGN_WARPS + warp;
     WarpRes wr;
     wr.smem_rows = smem + (size_t)warp * 2 * cfg.smem_cells;
-    wr.smem_cap = cfg.smem_cells;
+    wr.smem_cap = 2 * cfg.smem_cells;
     wr.grow = cfg.grow_cells > 0 ? grow_pool + slot * 2 * (size_t)cfg.grow_cells : nullptr;
     wr.grow_cap = cfg.grow_cells;
     wr.tb = tb_pool + slot * cfg.tb_words;
@@ -91,7 +91,7 @@ __global__ void k_banded_forward_dbg(const double *z, const long long *starts64,
     extern __shared__ double smem[];
     const int lane = tb2_lane();
     WarpRes wr;
-    wr.smem_rows = smem; wr.smem_cap = smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
+    wr.smem_rows = smem; wr.smem_cap = 2 * smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
     wr.tb = tbp; wr.tb_words = (size_t)nb * TB2_MAX_WPL * 32;
     DpConsts c;
     c.z_shift = 0; c.stay_pen = stay_pen; c.skip_pen = skip_pen; c.mhz = 0; c.winsor = 0;
@@ -100,16 +100,15 @@ __global__ void k_banded_forward_dbg(const double *z, const long long *starts64,
     pc.mso = 0; pc.msp_start = 0; pc.msp_stop = 0; pc.mask_fill = 0; pc.mask_shifted = 0;
     pc.starts = starts32; pc.tb = tbp; pc.dbg_fwd = fwd; pc.dbg_tb = tb64;
     int st = TB2_OK;
-    if (!tb2_setup_geom(pc, wr, W)) st = TB2_ERR_CAPACITY;
-    const int wpl = tb2_wpl_of(pc.chunk);
-    if (wpl > TB2_MAX_WPL) st = TB2_ERR_CAPACITY;
+    pc.W = W; pc.chunk = (W + 31) / 32; pc.buf0 = nullptr; pc.buf1 = nullptr;
+    double *rowbuf = tb2_wf_rowbuf(wr, W);
+    if (rowbuf == nullptr || (size_t)nb * tb2_wf_wpr(W) > wr.tb_words) st = TB2_ERR_CAPACITY;
     if (st == TB2_OK) {
         for (int r = lane; r < nb; r += 32) starts32[r] = (int)starts64[r];
         for (int j = lane; j < W; j += 32) { fwd[j] = 0.0; tb64[j] = 0; }
         __syncwarp();
-        int sel, amax = 0;
-        tb2_init_row0(pc, &sel);
-        st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_EXPLICIT, 0, nb, nb, &sel, &amax);
+        int amax = 0;
+        st = tb2_wavefront_rows(pc, c, TB2_MODE_EXPLICIT, nb, rowbuf, tbp, &amax);
     }
     if (lane == 0) *status = st;
 }
@@ -124,7 +123,7 @@ __global__ void k_adaptive_dbg(double *fwd, long long *tb64, long long *starts64
     extern __shared__ double smem[];
     const int lane = tb2_lane();
     WarpRes wr;
-    wr.smem_rows = smem; wr.smem_cap = smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
+    wr.smem_rows = smem; wr.smem_cap = 2 * smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
     wr.tb = tbp; wr.tb_words = (size_t)nb * TB2_MAX_WPL * 32;
     DpConsts c;
     c.z_shift = z_shift; c.stay_pen = stay_pen; c.skip_pen = skip_pen; c.mhz = mhz;
@@ -450,7 +449,7 @@ __global__ void k_single(int mode, const double *em, int n_em, const double *rm,
     extern __shared__ double smem[];
     const int lane = tb2_lane();
     WarpRes wr;
-    wr.smem_rows = smem; wr.smem_cap = smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
+    wr.smem_rows = smem; wr.smem_cap = 2 * smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
     wr.tb = tbp; wr.tb_words = tb_words;
     DpConsts c;
     c.z_shift = p.z_shift; c.stay_pen = p.stay_pen; c.skip_pen = p.skip_pen;

@@ -296,16 +296,16 @@ __device__ __forceinline__ uint32_t tb2_tb_code(const uint32_t (&w)[WPL], int bp
     return (v >> (2 * (i & 15))) & 3u;
 }
 
+// rows [row_lo, row_hi) in the lane-chunk layout; cur_event carried in and out
 template <int WPL>
-__device__ int tb2_traceback(const uint32_t *tb, const int *starts, int n_bases, int W,
-                             int chunk, int band_pos, int thresh, int *read_tb)
+__device__ int tb2_tb_seg_chunk(const uint32_t *tb, const int *starts, int row_hi, int row_lo,
+                                int W, int chunk, int thresh, int *cur_event_io, int *read_tb)
 {
     const int lane = tb2_lane();
-    int cur_event = band_pos + starts[n_bases - 1];
-    if (lane == 0) read_tb[n_bases] = cur_event + 1;
-    int sp = n_bases;
-    while (sp > 0) {
-        const int nblk = min(4, sp);
+    int cur_event = *cur_event_io;
+    int sp = row_hi;
+    while (sp > row_lo) {
+        const int nblk = min(4, sp - row_lo);
         uint32_t w[4][WPL];
         int st[4];
 #pragma unroll
@@ -338,6 +338,177 @@ __device__ int tb2_traceback(const uint32_t *tb, const int *starts, int n_bases,
         }
         sp -= nblk;
     }
+    *cur_event_io = cur_event;
+    __syncwarp();
+    return TB2_OK;
+}
+
+// ===========================================================================
+// Wavefront engine for STATIC bands (band starts known up front: short-read
+// static band, start search, masked start, mirror API).
+//
+// Lane L of a 32-row strip owns row s0+L and walks its band left to right; at
+// step t it handles event e = t - L, so the cell above (row-1, e) was produced by
+// lane L-1 one step earlier and arrives by a single shuffle, and (row-1, e-1) is
+// the value received the step before.  Every cell is evaluated exactly once with
+// the reference's operations (no speculation, no re-association): bit-exact by
+// construction.  Strips are chained through one row buffer in shared memory
+// (writes of the strip's last row trail the reads of its first row by >= 31
+// cells).  Event means are read coalesced (32 consecutive events per step).
+// Moves: 2 bits/cell, row-major u32 words  tb[row * wpr + (j >> 4)].
+// ===========================================================================
+struct WfOut {
+    int argmax;        // first arg-max of row r_end-1
+};
+
+__device__ __forceinline__ int tb2_wf_wpr(int W) { return (W + 15) >> 4; }
+
+__device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode, int r_end,
+                                  double *rowbuf, uint32_t *tbw, int *argmax_out)
+{
+    const int lane = tb2_lane();
+    const int W = pc.W, wpr = tb2_wf_wpr(W);
+    const double NEG = tb2_neg_inf();
+    double best = NEG;
+    int best_idx = 0x7fffffff;
+    for (int s0 = 0; s0 < r_end; s0 += 32) {
+        const int r = s0 + lane;
+        const bool row_ok = r < r_end;
+        const int lane_last = min(31, r_end - 1 - s0);
+        const int start = row_ok ? pc.starts[r] : 0;
+        const int prev_start = (row_ok && r > 0) ? pc.starts[r - 1] : start;
+        const int d = start - prev_start;
+        const double mu = (row_ok && pc.rm) ? __ldg(pc.rm + r) : 0.0;
+        const double sd = (row_ok && pc.rs_) ? __ldg(pc.rs_ + r) : 1.0;
+        int lo = 0, hi = W;
+        double maskval = pc.mask_fill;
+        if (mode == TB2_MODE_MASKED && row_ok) {
+            const int sml = max(pc.mso - start, 0);
+            int eml = 0;
+            if (r < TB2_MASK_BASES)
+                eml = W - ((int)tb2_linspace_at(pc.msp_start, pc.msp_stop, TB2_MASK_BASES, r) - start);
+            if (start + W - eml > pc.n_em) eml = start + W - pc.n_em;
+            lo = sml; hi = W - eml; maskval = pc.mask_shifted;
+        }
+        const double *zrow = (mode == TB2_MODE_EXPLICIT && row_ok) ? pc.zmat + (size_t)r * W : nullptr;
+        const bool first_skip = (r == 0) || (d == 0);
+        const bool is_tail = row_ok && (lane == lane_last);       // feeds the next strip
+        const bool want_best = row_ok && (r == r_end - 1);
+        const int t_begin = __shfl_sync(TB2_FULL_MASK, start, 0);
+        const int t_end = __shfl_sync(TB2_FULL_MASK, start, lane_last) + W - 1 + lane_last;
+        double x = 0.0, xout = 0.0, up_prev = 0.0;
+        uint32_t cw = 0u;
+        for (int t = t_begin; t <= t_end; ++t) {
+            double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);
+            const int e = t - lane;
+            const int j = e - start;
+            const int p = j + d;
+            double upl = up_prev;
+            if (lane == 0) {
+                // row above = last row of the previous strip (rowbuf, band coordinates of
+                // that row); (row-1, e-1) is carried in a register like on the other
+                // lanes, because this strip's tail row overwrites rowbuf behind us
+                if (s0 == 0) { up = 0.0; upl = 0.0; }
+                else {
+                    up = (p >= 0 && p < W) ? rowbuf[p] : NEG;
+                    if (j == 0) upl = (p >= 1 && p - 1 < W) ? rowbuf[p - 1] : NEG;
+                }
+            }
+            up_prev = up;
+            if (row_ok && j >= 0 && j < W) {
+                double z;
+                if (zrow) z = zrow[j];
+                else if (j < lo || j >= hi) z = maskval;
+                else {
+                    double a = fabs(__ldg(pc.em + e) - mu) / sd;
+                    if (c.winsor) a = (c.mhz < a) ? c.mhz : a;
+                    z = c.z_shift - a;
+                }
+                const double u = (p < W) ? up : NEG;                   // (row-1, e)
+                const double ul = (p >= 1 && p - 1 < W) ? upl : NEG;   // (row-1, e-1)
+                double nx;
+                uint32_t code;
+                if (j == 0) {
+                    if (first_skip) { nx = u - c.skip_pen; code = 1u; }
+                    else { nx = ul + z; code = 2u; }
+                } else {
+                    const double a = (x - c.stay_pen) + z;
+                    double cc = ul + z;
+                    uint32_t cf = 2u;
+                    const double sk = u - c.skip_pen;
+                    if (sk > cc) { cc = sk; cf = 1u; }
+                    if (cc > a) { nx = cc; code = cf; }
+                    else { nx = a; code = 0u; }
+                }
+                x = nx;
+                xout = nx;
+                cw |= code << (2 * (j & 15));
+                if ((j & 15) == 15 || j == W - 1) { tbw[(size_t)r * wpr + (j >> 4)] = cw; cw = 0u; }
+                if (is_tail) rowbuf[j] = nx;
+                if (want_best && nx > best) { best = nx; best_idx = j; }
+                if (pc.dbg_fwd) {
+                    pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;
+                    pc.dbg_tb[(size_t)(r + 1) * W + j] = code;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    *argmax_out = tb2_warp_argmax(best, best_idx);
+    return TB2_OK;
+}
+
+// traceback over rows [row_lo, row_hi) stored in the wavefront layout; cur_event is
+// carried in and out (c_banded_traceback _c_dynamic_programming.pyx:295-308).
+// Lanes prefetch three words around the expected band position of 32 rows at once.
+__device__ int tb2_tb_seg_wf(const uint32_t *tbw, int wpr, const int *starts, int row_hi,
+                             int row_lo, int W, int thresh, int *cur_event_io, int *read_tb)
+{
+    const int lane = tb2_lane();
+    int cur_event = *cur_event_io;
+    while (row_hi > row_lo) {
+        const int nblk = min(32, row_hi - row_lo);
+        const int my_row = row_hi - 1 - lane;
+        int my_start = 0, base = 0;
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (lane < nblk) {
+            my_start = starts[my_row];
+            const int est = cur_event - lane - my_start;
+            base = min(max((est >> 4) - 1, 0), max(wpr - 3, 0));
+            const uint32_t *rw = tbw + (size_t)my_row * wpr;
+            w0 = rw[base];
+            if (base + 1 < wpr) w1 = rw[base + 1];
+            if (base + 2 < wpr) w2 = rw[base + 2];
+        }
+        for (int k = 0; k < nblk; ++k) {
+            const int row = row_hi - 1 - k;
+            const int st = __shfl_sync(TB2_FULL_MASK, my_start, k);
+            const int bs = __shfl_sync(TB2_FULL_MASK, base, k);
+            int bp = cur_event - st;
+            if (bp < 0 || bp >= W) return TB2_ERR_UNEXPECTED;
+            uint32_t code;
+            for (;;) {
+                const int wi = bp >> 4, rel = wi - bs;
+                uint32_t v;
+                if (rel >= 0 && rel < 3) {
+                    const uint32_t mine = rel == 0 ? w0 : (rel == 1 ? w1 : w2);
+                    v = __shfl_sync(TB2_FULL_MASK, mine, k);
+                } else {
+                    v = tbw[(size_t)row * wpr + wi];
+                }
+                code = (v >> (2 * (bp & 15))) & 3u;
+                if (code != 0u) break;
+                --bp;
+                if (bp < 0) return TB2_ERR_UNEXPECTED;
+            }
+            if (code == 2u) --bp;
+            if (thresh >= 0 && min(bp, W - bp - 1) < thresh) return TB2_ERR_BEYOND_BANDWIDTH;
+            cur_event = st + bp;
+            if (lane == 0) read_tb[row] = cur_event + 1;
+        }
+        row_hi -= nblk;
+    }
+    *cur_event_io = cur_event;
     __syncwarp();
     return TB2_OK;
 }

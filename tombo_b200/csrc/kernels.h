@@ -41,6 +41,8 @@ static inline size_t tb2_tb_words(long long rows, long long W)
     long long chunk = (W + 31) / 32;
     long long wpl = (chunk + 15) / 16;
     wpl = wpl <= 5 ? wpl : (wpl <= 8 ? 8 : 16);   // instantiated widths (tb2_wpl_of)
-    return (size_t)(rows * wpl * 32);
+    // lane-chunk rows (wpl * 32 words) plus wavefront rows (ceil(W/16) words): an
+    // upper bound valid for every mix of the two engines
+    return (size_t)(rows * wpl * 32 + rows * ((W + 15) / 16));
 }
 static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }

@@ -140,11 +140,13 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
         const bool is_short = n_em < p.start_bw + p.start_n_bases || nb < p.start_n_bases;
         if (is_short) {
             if (tb2_row_cells(w_static) / 32 > TB2_MAX_CHUNK) continue;  // CAPACITY status on device
-            cfg->smem_cells = std::max(cfg->smem_cells, tb2_row_cells(w_static));
+            // static band: one plain row (wavefront engine); smem_cells counts pairs
+            cfg->smem_cells = std::max(cfg->smem_cells, tb2_row_cells((w_static + 1) / 2));
             cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(nb, w_static));
         } else {
             cfg->smem_cells = std::max(cfg->smem_cells,
-                                       tb2_row_cells(std::max<long long>(p.start_bw, p.bandwidth)));
+                                       tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2,
+                                                                         p.bandwidth)));
             cfg->tb_words = std::max(cfg->tb_words, std::max(tb2_tb_words(nb, p.bandwidth),
                                                              tb2_tb_words(p.start_n_bases, p.start_bw)));
             if (n_em >= p.start_save_bw + p.start_n_bases) {
