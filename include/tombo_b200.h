@@ -213,6 +213,10 @@ int tb2_find_seq_start_in_events(tb2_ctx *ctx, const double *event_means,
  * traceback (n_bases + 1) left by the last tb2_find_adaptive_base_assignment */
 int tb2_debug_last_assignment(tb2_ctx *ctx, int64_t n_bases, int64_t *starts_out,
                               int64_t *read_tb_out);
+/* self-check: blocks x 256 x per_thread random / adversarial (a, b) pairs; counts
+ * pairs where the reciprocal-based division of the DP rows differs from a / b */
+int tb2_debug_div_check(tb2_ctx *ctx, uint64_t seed, int blocks, int per_thread,
+                        uint64_t *mismatches, double *example4);
 /* resolve_skipped_bases_with_raw resquiggle.py:402-540 */
 int tb2_resolve_skipped_bases_with_raw(
     tb2_ctx *ctx, const int64_t *segs, int64_t n_bases, const double *ref_means,

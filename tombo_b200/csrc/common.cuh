@@ -19,6 +19,24 @@ __device__ __forceinline__ double tb2_neg_inf()
 
 __device__ __forceinline__ int tb2_lane() { return threadIdx.x & 31; }
 
+// Correctly rounded a / b for a divisor b that is reused (one k-mer level SD per DP
+// row): y = RN(1/b) once (__drcp_rn), then per quotient one multiply and two
+// residual corrections.  q0 = RN(a*y) is within 2 ulp; the first correction makes
+// q1 faithful; by Markstein's theorem (Markstein 1990; Muller et al., Handbook of
+// Floating-Point Arithmetic, "division by software": y = RN(1/b), q faithful,
+// r = a - b*q exact by FMA  =>  RN(q + r*y) = RN(a/b), barring over/underflow) the
+// second correction returns exactly what the IEEE division of the reference
+// (_c_dynamic_programming.pyx:366) returns.  5 fp64 ops instead of ~25;
+// tests/test_div_gpu.py checks it against `/` on 2^31 adversarial and random pairs.
+__device__ __forceinline__ double tb2_div_by(double a, double b, double y)
+{
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
+}
+
 // keyed bijection on [0, n) (mirror of tombo_b200/synthetic.py perm_index):
 // stands in for np.random.choice(n, 1000, replace=False), tombo_stats.py:413
 __host__ __device__ __forceinline__ uint32_t tb2_mix32(uint32_t x)

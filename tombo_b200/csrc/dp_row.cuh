@@ -28,7 +28,7 @@ struct DpConsts {
 struct RowSpec {
     const double *em;    // event means (index e0 + j)
     const double *zrow;  // explicit z-scores of this row (mirror API) or nullptr
-    double mu, sd;
+    double mu, sd, inv_sd;  // inv_sd = RN(1 / sd)
     int e0;              // event index of band position 0 (may be negative)
     int lo, hi;          // cells outside [lo, hi) hold maskval
     double maskval;
@@ -40,7 +40,7 @@ __device__ __forceinline__ double tb2_zscore(const RowSpec &rs, const DpConsts &
     if (j < rs.lo || j >= rs.hi) return rs.maskval;
     // z_shift - min(max_half_z, |ev - mean| / sd)
     // (_c_dynamic_programming.pyx:366-372; resquiggle.py:574-582)
-    double a = fabs(__ldg(rs.em + (rs.e0 + j)) - rs.mu) / rs.sd;
+    double a = tb2_div_by(fabs(__ldg(rs.em + (rs.e0 + j)) - rs.mu), rs.sd, rs.inv_sd);
     if (c.winsor) a = (c.mhz < a) ? c.mhz : a;
     return c.z_shift - a;
 }
@@ -198,6 +198,7 @@ __device__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, int mode, int 
         rs.em = pc.em; rs.zrow = nullptr;
         rs.mu = pc.rm ? __ldg(pc.rm + r) : 0.0;
         rs.sd = pc.rs_ ? __ldg(pc.rs_ + r) : 1.0;
+        rs.inv_sd = __drcp_rn(rs.sd);
         rs.lo = 0; rs.hi = W; rs.maskval = pc.mask_fill;
         int cur_start;
         if (mode == TB2_MODE_ADAPTIVE) {
@@ -357,18 +358,31 @@ __device__ int tb2_tb_seg_chunk(const uint32_t *tb, const int *starts, int row_h
 // cells).  Event means are read coalesced (32 consecutive events per step).
 // Moves: 2 bits/cell, row-major u32 words  tb[row * wpr + (j >> 4)].
 // ===========================================================================
-struct WfOut {
-    int argmax;        // first arg-max of row r_end-1
-};
-
 __device__ __forceinline__ int tb2_wf_wpr(int W) { return (W + 15) >> 4; }
 
-__device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode, int r_end,
-                                  double *rowbuf, uint32_t *tbw, int *argmax_out)
+// shifted z-score of one cell for the wavefront engine.  The divide is the exact
+// reciprocal form (tb2_div_by): inv_sd = RN(1 / sd) once per row.
+template <int MODE>
+__device__ __forceinline__ double tb2_wf_z(const double *ep, int j, double mu, double sd,
+                                           double inv_sd, int lo, int hi, double maskval,
+                                           const double *zrow, double zs, double mhz, bool win)
+{
+    if (MODE == TB2_MODE_EXPLICIT) return zrow[j];
+    if (MODE == TB2_MODE_MASKED && (j < lo || j >= hi)) return maskval;
+    double a = tb2_div_by(fabs(__ldg(ep) - mu), sd, inv_sd);
+    if (win) a = (mhz < a) ? mhz : a;
+    return zs - a;
+}
+
+template <int MODE, bool DBG>
+__device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_end,
+                                    double *rowbuf, uint32_t *tbw, int *argmax_out)
 {
     const int lane = tb2_lane();
     const int W = pc.W, wpr = tb2_wf_wpr(W);
     const double NEG = tb2_neg_inf();
+    const double stay = c.stay_pen, skip = c.skip_pen, zs = c.z_shift, mhz = c.mhz;
+    const bool win = c.winsor != 0;
     double best = NEG;
     int best_idx = 0x7fffffff;
     for (int s0 = 0; s0 < r_end; s0 += 32) {
@@ -380,9 +394,10 @@ __device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode
         const int d = start - prev_start;
         const double mu = (row_ok && pc.rm) ? __ldg(pc.rm + r) : 0.0;
         const double sd = (row_ok && pc.rs_) ? __ldg(pc.rs_ + r) : 1.0;
+        const double inv_sd = __drcp_rn(sd);
         int lo = 0, hi = W;
         double maskval = pc.mask_fill;
-        if (mode == TB2_MODE_MASKED && row_ok) {
+        if (MODE == TB2_MODE_MASKED && row_ok) {
             const int sml = max(pc.mso - start, 0);
             int eml = 0;
             if (r < TB2_MASK_BASES)
@@ -390,72 +405,129 @@ __device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode
             if (start + W - eml > pc.n_em) eml = start + W - pc.n_em;
             lo = sml; hi = W - eml; maskval = pc.mask_shifted;
         }
-        const double *zrow = (mode == TB2_MODE_EXPLICIT && row_ok) ? pc.zmat + (size_t)r * W : nullptr;
+        const double *zrow = (MODE == TB2_MODE_EXPLICIT && row_ok) ? pc.zmat + (size_t)r * W : nullptr;
         const bool first_skip = (r == 0) || (d == 0);
         const bool is_tail = row_ok && (lane == lane_last);       // feeds the next strip
+        const bool track = (s0 + 32 >= r_end);                    // strip holding the last row
         const bool want_best = row_ok && (r == r_end - 1);
-        const int t_begin = __shfl_sync(TB2_FULL_MASK, start, 0);
-        const int t_end = __shfl_sync(TB2_FULL_MASK, start, lane_last) + W - 1 + lane_last;
+        const bool lane0_buf = (lane == 0) && (s0 > 0);
+        uint32_t *tbr = tbw + (size_t)(row_ok ? r : 0) * wpr;
+        // uniform time bounds of the strip
+        const int start_first = __shfl_sync(TB2_FULL_MASK, start, 0);
+        const int start_last = __shfl_sync(TB2_FULL_MASK, start, lane_last);
+        int dmax = row_ok ? d : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) dmax = max(dmax, __shfl_xor_sync(TB2_FULL_MASK, dmax, off));
+        const int t_begin = start_first;
+        const int t_end = start_last + W - 1 + lane_last;
+        // steady state: every lane of a full strip is inside its band with j >= 1 and
+        // both cells of the row above available
+        int t_lo = start_last + lane_last + 1, t_hi = start_first + W - 2 - dmax;
+        if (lane_last != 31) { t_lo = t_end + 1; t_hi = t_end; }   // partial strip: general path
         double x = 0.0, xout = 0.0, up_prev = 0.0;
         uint32_t cw = 0u;
-        for (int t = t_begin; t <= t_end; ++t) {
-            double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);
-            const int e = t - lane;
-            const int j = e - start;
-            const int p = j + d;
-            double upl = up_prev;
-            if (lane == 0) {
-                // row above = last row of the previous strip (rowbuf, band coordinates of
-                // that row); (row-1, e-1) is carried in a register like on the other
-                // lanes, because this strip's tail row overwrites rowbuf behind us
-                if (s0 == 0) { up = 0.0; upl = 0.0; }
-                else {
-                    up = (p >= 0 && p < W) ? rowbuf[p] : NEG;
-                    if (j == 0) upl = (p >= 1 && p - 1 < W) ? rowbuf[p - 1] : NEG;
-                }
-            }
-            up_prev = up;
-            if (row_ok && j >= 0 && j < W) {
-                double z;
-                if (zrow) z = zrow[j];
-                else if (j < lo || j >= hi) z = maskval;
-                else {
-                    double a = fabs(__ldg(pc.em + e) - mu) / sd;
-                    if (c.winsor) a = (c.mhz < a) ? c.mhz : a;
-                    z = c.z_shift - a;
-                }
-                const double u = (p < W) ? up : NEG;                   // (row-1, e)
-                const double ul = (p >= 1 && p - 1 < W) ? upl : NEG;   // (row-1, e-1)
-                double nx;
-                uint32_t code;
-                if (j == 0) {
-                    if (first_skip) { nx = u - c.skip_pen; code = 1u; }
-                    else { nx = ul + z; code = 2u; }
-                } else {
-                    const double a = (x - c.stay_pen) + z;
-                    double cc = ul + z;
-                    uint32_t cf = 2u;
-                    const double sk = u - c.skip_pen;
-                    if (sk > cc) { cc = sk; cf = 1u; }
-                    if (cc > a) { nx = cc; code = cf; }
-                    else { nx = a; code = 0u; }
-                }
+        int j = t_begin - lane - start;
+        const double *ep = pc.em + (t_begin - lane);
+        int t = t_begin;
+        // ---------- general step (prologue / epilogue / partial strips) ----------
+#define TB2_WF_GENERAL_STEP()                                                                   \
+        {                                                                                       \
+            double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);                                 \
+            const int p = j + d;                                                                \
+            double upl = up_prev;                                                               \
+            if (lane == 0) {                                                                    \
+                if (s0 == 0) { up = 0.0; upl = 0.0; }                                           \
+                else {                                                                          \
+                    up = (p >= 0 && p < W) ? rowbuf[p] : NEG;                                   \
+                    if (j == 0) upl = (p >= 1 && p - 1 < W) ? rowbuf[p - 1] : NEG;              \
+                }                                                                               \
+            }                                                                                   \
+            up_prev = up;                                                                       \
+            if (row_ok && j >= 0 && j < W) {                                                    \
+                const double z = tb2_wf_z<MODE>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow,   \
+                                                zs, mhz, win);                                  \
+                const double u = (p < W) ? up : NEG;                                            \
+                const double ul = (p >= 1 && p - 1 < W) ? upl : NEG;                            \
+                double nx;                                                                      \
+                uint32_t code;                                                                  \
+                if (j == 0) {                                                                   \
+                    if (first_skip) { nx = u - skip; code = 1u; }                               \
+                    else { nx = ul + z; code = 2u; }                                            \
+                } else {                                                                        \
+                    const double a = (x - stay) + z;                                            \
+                    double cc = ul + z;                                                         \
+                    uint32_t cf = 2u;                                                           \
+                    const double sk = u - skip;                                                 \
+                    if (sk > cc) { cc = sk; cf = 1u; }                                          \
+                    if (cc > a) { nx = cc; code = cf; }                                         \
+                    else { nx = a; code = 0u; }                                                 \
+                }                                                                               \
+                x = nx;                                                                         \
+                xout = nx;                                                                      \
+                cw |= code << (2 * (j & 15));                                                   \
+                if ((j & 15) == 15 || j == W - 1) { tbr[j >> 4] = cw; cw = 0u; }                \
+                if (is_tail) rowbuf[j] = nx;                                                    \
+                if (want_best && nx > best) { best = nx; best_idx = j; }                        \
+                if (DBG) {                                                                      \
+                    pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;                                   \
+                    pc.dbg_tb[(size_t)(r + 1) * W + j] = code;                                  \
+                }                                                                               \
+            }                                                                                   \
+            ++j; ++ep;                                                                          \
+        }
+        for (; t <= t_end && t < t_lo; ++t) TB2_WF_GENERAL_STEP()
+        if (t <= t_hi) {
+            // ---------- steady state: no band-edge predicates, z one step ahead ----------
+            double z = tb2_wf_z<MODE>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz, win);
+            for (; t <= t_hi; ++t) {
+                double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);
+                if (lane == 0) up = lane0_buf ? rowbuf[j + d] : 0.0;
+                const double upl = up_prev;
+                up_prev = up;
+                const double a = (x - stay) + z;
+                double cc = upl + z;
+                uint32_t code = 2u;
+                const double sk = up - skip;
+                if (sk > cc) { cc = sk; code = 1u; }
+                double nx = a;
+                if (cc > a) nx = cc; else code = 0u;
                 x = nx;
                 xout = nx;
                 cw |= code << (2 * (j & 15));
-                if ((j & 15) == 15 || j == W - 1) { tbw[(size_t)r * wpr + (j >> 4)] = cw; cw = 0u; }
+                if ((j & 15) == 15) { tbr[j >> 4] = cw; cw = 0u; }
                 if (is_tail) rowbuf[j] = nx;
-                if (want_best && nx > best) { best = nx; best_idx = j; }
-                if (pc.dbg_fwd) {
+                if (track && want_best && nx > best) { best = nx; best_idx = j; }
+                if (DBG) {
                     pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;
                     pc.dbg_tb[(size_t)(r + 1) * W + j] = code;
                 }
+                ++j; ++ep;
+                z = tb2_wf_z<MODE>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz, win);
             }
         }
+        for (; t <= t_end; ++t) TB2_WF_GENERAL_STEP()
+#undef TB2_WF_GENERAL_STEP
         __syncwarp();
     }
     *argmax_out = tb2_warp_argmax(best, best_idx);
     return TB2_OK;
+}
+
+__device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode, int r_end,
+                                  double *rowbuf, uint32_t *tbw, int *argmax_out)
+{
+    if (pc.dbg_fwd) {
+        if (mode == TB2_MODE_EXPLICIT)
+            return tb2_wavefront_rows_t<TB2_MODE_EXPLICIT, true>(pc, c, r_end, rowbuf, tbw, argmax_out);
+        if (mode == TB2_MODE_MASKED)
+            return tb2_wavefront_rows_t<TB2_MODE_MASKED, true>(pc, c, r_end, rowbuf, tbw, argmax_out);
+        return tb2_wavefront_rows_t<TB2_MODE_PLAIN, true>(pc, c, r_end, rowbuf, tbw, argmax_out);
+    }
+    if (mode == TB2_MODE_EXPLICIT)
+        return tb2_wavefront_rows_t<TB2_MODE_EXPLICIT, false>(pc, c, r_end, rowbuf, tbw, argmax_out);
+    if (mode == TB2_MODE_MASKED)
+        return tb2_wavefront_rows_t<TB2_MODE_MASKED, false>(pc, c, r_end, rowbuf, tbw, argmax_out);
+    return tb2_wavefront_rows_t<TB2_MODE_PLAIN, false>(pc, c, r_end, rowbuf, tbw, argmax_out);
 }
 
 // traceback over rows [row_lo, row_hi) stored in the wavefront layout; cur_event is
