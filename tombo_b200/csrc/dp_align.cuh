@@ -132,7 +132,7 @@ __device__ int tb2_static_pass(PassCtx &pc, const WarpRes &wr, const DpConsts &c
 }
 
 // find_seq_start_in_events resquiggle.py:685-752
-__device__ int tb2_start_find(const AlignRead &a, const WarpRes &wr, const DpConsts &c,
+__device__ __noinline__ int tb2_start_find(const AlignRead &a, const WarpRes &wr, const DpConsts &c,
                               int num_bases, int num_events, bool check_score,
                               double sig_match_thresh, int *start_loc, double *epb)
 {
@@ -195,7 +195,7 @@ __device__ int tb2_emit_segs(const AlignRead &a, const int *cpts, int n_idx)
 }
 
 // find_static_base_assignment resquiggle.py:547-600 + get_short_read_results
-__device__ int tb2_static_assign(const AlignRead &a, const WarpRes &wr, const DpConsts &c,
+__device__ __noinline__ int tb2_static_assign(const AlignRead &a, const WarpRes &wr, const DpConsts &c,
                                  bool emit_segs = true)
 {
     const int lane = tb2_lane();

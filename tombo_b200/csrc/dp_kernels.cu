@@ -8,6 +8,10 @@
 // ---------------------------------------------------------------------------
 // production kernel: persistent warps, one read per warp at a time
 // ---------------------------------------------------------------------------
+// KLASS 1 is the lean kernel for reads that can only take the static-band path
+// (find_adaptive_base_assignment resquiggle.py:986-989): wavefront engine only, so
+// fewer registers and twice the resident warps of the general kernel.
+template <int KLASS>
 __global__ void __launch_bounds__(ALIGN_WARPS * 32)
 k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, int *counter)
 {
@@ -29,6 +33,12 @@ k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, 
         const size_t ix = (size_t)r * b.stride;
         if (b.status[ix] != TB2_OK) continue;
         if (b.active && !b.active[ix]) continue;
+        if (KLASS != 0) {
+            const int nbr = (int)(b.base_off[r + 1] - b.base_off[r]);
+            const bool is_short = (b.num_events[ix] - 1 < b.params.start_bw + b.params.start_n_bases) ||
+                                  (nbr < b.params.start_n_bases);
+            if (is_short != (KLASS == 1)) continue;
+        }
         AlignRead a;
         const long long eo = b.ev_off[r], bo = b.base_off[r];
         a.cpts = b.cpts + eo;
@@ -42,7 +52,18 @@ k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, 
         a.segs = b.segs + bo + r;
         a.rsrtr = b.rsrtr + ix;
         a.dbg = b.dbg ? b.dbg + 3 * (size_t)r : nullptr;
-        const int st = tb2_align_read(a, wr, b.params, b.sig_match_thresh);
+        int st;
+        if (KLASS == 1) {
+            DpConsts c;
+            c.z_shift = b.params.z_shift; c.stay_pen = b.params.stay_pen;
+            c.skip_pen = b.params.skip_pen;
+            c.winsor = !isnan(b.params.max_half_z_score);
+            c.mhz = c.winsor ? b.params.max_half_z_score : 0.0;
+            if (a.dbg && lane == 0) { a.dbg[0] = 0; a.dbg[1] = -1; a.dbg[2] = -1; }
+            st = (a.n_cpts - 1 < 1 || a.nb < 1) ? TB2_ERR_UNEXPECTED : tb2_static_assign(a, wr, c);
+        } else {
+            st = tb2_align_read(a, wr, b.params, b.sig_match_thresh);
+        }
         __syncwarp();
         if (lane == 0) b.status[ix] = st;
     }
@@ -61,7 +82,8 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
         cfg.smem_cells = cap;
         smem = (size_t)ALIGN_WARPS * 2 * cfg.smem_cells * sizeof(double);
     }
-    int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem, 1)));
+    const int max_blocks = cfg.klass == 1 ? 8 : 4;
+    int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(max_blocks, (220 * 1024) / std::max<size_t>(smem, 1)));
     int grid = ctx->sm_count * blocks_per_sm;
     const int max_useful = (b.n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS;
     if (grid > max_useful) grid = std::max(1, max_useful);
@@ -71,9 +93,10 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_GROW].reserve(slots * 2 * (size_t)cfg.grow_cells * sizeof(double) + 8));
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT].reserve(sizeof(int)));
     TB2_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool[SLOT_CNT].p, 0, sizeof(int), ctx->stream));
-    TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    auto kern = cfg.klass == 1 ? k_align<1> : (cfg.klass == 2 ? k_align<2> : k_align<0>);
+    TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
-    k_align<<<grid, ALIGN_WARPS * 32, smem, ctx->stream>>>(
+    kern<<<grid, ALIGN_WARPS * 32, smem, ctx->stream>>>(
         b, cfg, ctx->pool[SLOT_TB].as<uint32_t>(), ctx->pool[SLOT_GROW].as<double>(),
         ctx->pool[SLOT_CNT].as<int>());
     TB2_CHECK_LAUNCH(ctx);
@@ -397,11 +420,12 @@ extern "C" int tb2_find_adaptive_base_assignment(
     b.rsrtr = P[S_G].as<int>() + 2;
     b.status = P[S_G].as<int>() + 1;
     b.active = nullptr;
+    b.num_events = nullptr;
     b.stride = 1;
     b.dbg = P[S_G].as<int>() + 3;
     b.params = *params;
     b.sig_match_thresh = sig_match_thresh;
-    AlignLaunchCfg cfg = {32, 32, 0};
+    AlignLaunchCfg cfg = {32, 32, 0, 0};
     plan_align(*params, n_em, nb, &cfg.smem_cells, &cfg.tb_words, &cfg.grow_cells);
     // the single-read mirror also covers the rare static fall-back of long reads
     cfg.tb_words = std::max(cfg.tb_words, tb2_tb_words(nb, std::max<long long>(1, n_em - std::min(nb, n_em) / 4)));

@@ -183,7 +183,7 @@ struct PassCtx {
 // (TB2_OK or TB2_ERR_ADAPTIVE_BEYOND_SIGNAL); on return *cur_sel selects the
 // buffer holding fwd row r_end and (best_idx_out) its first arg-max.
 template <int WPL>
-__device__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, int mode, int r_begin,
+__device__ __noinline__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, int mode, int r_begin,
                             int r_end, int n_bases_total, int *cur_sel, int *argmax_out)
 {
     const int lane = tb2_lane();
@@ -299,7 +299,7 @@ __device__ __forceinline__ uint32_t tb2_tb_code(const uint32_t (&w)[WPL], int bp
 
 // rows [row_lo, row_hi) in the lane-chunk layout; cur_event carried in and out
 template <int WPL>
-__device__ int tb2_tb_seg_chunk(const uint32_t *tb, const int *starts, int row_hi, int row_lo,
+__device__ __noinline__ int tb2_tb_seg_chunk(const uint32_t *tb, const int *starts, int row_hi, int row_lo,
                                 int W, int chunk, int thresh, int *cur_event_io, int *read_tb)
 {
     const int lane = tb2_lane();
@@ -362,35 +362,53 @@ __device__ __forceinline__ int tb2_wf_wpr(int W) { return (W + 15) >> 4; }
 
 // shifted z-score of one cell for the wavefront engine.  The divide is the exact
 // reciprocal form (tb2_div_by): inv_sd = RN(1 / sd) once per row.
-template <int MODE>
+template <int MODE, bool WIN>
 __device__ __forceinline__ double tb2_wf_z(const double *ep, int j, double mu, double sd,
                                            double inv_sd, int lo, int hi, double maskval,
-                                           const double *zrow, double zs, double mhz, bool win)
+                                           const double *zrow, double zs, double mhz)
 {
     if (MODE == TB2_MODE_EXPLICIT) return zrow[j];
     if (MODE == TB2_MODE_MASKED && (j < lo || j >= hi)) return maskval;
     double a = tb2_div_by(fabs(__ldg(ep) - mu), sd, inv_sd);
-    if (win) a = (mhz < a) ? mhz : a;
+    if (WIN) a = (mhz < a) ? mhz : a;
     return zs - a;
 }
 
-template <int MODE, bool DBG>
-__device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_end,
-                                    double *rowbuf, uint32_t *tbw, int *argmax_out)
+// strip-chaining row buffer: shared-memory accesses when it lives in shared memory
+template <bool RBS>
+__device__ __forceinline__ double tb2_rb_ld(const double *rb, unsigned rb_s, int i)
+{
+    if (RBS) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(rb_s + 8u * (unsigned)i));
+        return v;
+    }
+    return rb[i];
+}
+template <bool RBS>
+__device__ __forceinline__ void tb2_rb_st(double *rb, unsigned rb_s, int i, double v)
+{
+    if (RBS) asm volatile("st.shared.f64 [%0], %1;" ::"r"(rb_s + 8u * (unsigned)i), "d"(v));
+    else rb[i] = v;
+}
+
+template <int MODE, bool DBG, bool WIN, bool RBS>
+__device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_end,
+                                                 double *rowbuf, uint32_t *tbw, int *argmax_out)
 {
     const int lane = tb2_lane();
     const int W = pc.W, wpr = tb2_wf_wpr(W);
     const double NEG = tb2_neg_inf();
     const double stay = c.stay_pen, skip = c.skip_pen, zs = c.z_shift, mhz = c.mhz;
-    const bool win = c.winsor != 0;
-    double best = NEG;
-    int best_idx = 0x7fffffff;
+    const unsigned rb_s = RBS ? (unsigned)__cvta_generic_to_shared(rowbuf) : 0u;
+    const double *em = pc.em;
+    const int *starts = pc.starts;
     for (int s0 = 0; s0 < r_end; s0 += 32) {
         const int r = s0 + lane;
         const bool row_ok = r < r_end;
         const int lane_last = min(31, r_end - 1 - s0);
-        const int start = row_ok ? pc.starts[r] : 0;
-        const int prev_start = (row_ok && r > 0) ? pc.starts[r - 1] : start;
+        const int start = row_ok ? starts[r] : 0;
+        const int prev_start = (row_ok && r > 0) ? starts[r - 1] : start;
         const int d = start - prev_start;
         const double mu = (row_ok && pc.rm) ? __ldg(pc.rm + r) : 0.0;
         const double sd = (row_ok && pc.rs_) ? __ldg(pc.rs_ + r) : 1.0;
@@ -408,8 +426,6 @@ __device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_
         const double *zrow = (MODE == TB2_MODE_EXPLICIT && row_ok) ? pc.zmat + (size_t)r * W : nullptr;
         const bool first_skip = (r == 0) || (d == 0);
         const bool is_tail = row_ok && (lane == lane_last);       // feeds the next strip
-        const bool track = (s0 + 32 >= r_end);                    // strip holding the last row
-        const bool want_best = row_ok && (r == r_end - 1);
         const bool lane0_buf = (lane == 0) && (s0 > 0);
         uint32_t *tbr = tbw + (size_t)(row_ok ? r : 0) * wpr;
         // uniform time bounds of the strip
@@ -427,7 +443,7 @@ __device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_
         double x = 0.0, xout = 0.0, up_prev = 0.0;
         uint32_t cw = 0u;
         int j = t_begin - lane - start;
-        const double *ep = pc.em + (t_begin - lane);
+        const double *ep = em + (t_begin - lane);
         int t = t_begin;
         // ---------- general step (prologue / epilogue / partial strips) ----------
 #define TB2_WF_GENERAL_STEP()                                                                   \
@@ -438,14 +454,14 @@ __device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_
             if (lane == 0) {                                                                    \
                 if (s0 == 0) { up = 0.0; upl = 0.0; }                                           \
                 else {                                                                          \
-                    up = (p >= 0 && p < W) ? rowbuf[p] : NEG;                                   \
-                    if (j == 0) upl = (p >= 1 && p - 1 < W) ? rowbuf[p - 1] : NEG;              \
+                    up = (p >= 0 && p < W) ? tb2_rb_ld<RBS>(rowbuf, rb_s, p) : NEG;             \
+                    if (j == 0) upl = (p >= 1 && p - 1 < W) ? tb2_rb_ld<RBS>(rowbuf, rb_s, p - 1) : NEG; \
                 }                                                                               \
             }                                                                                   \
             up_prev = up;                                                                       \
             if (row_ok && j >= 0 && j < W) {                                                    \
-                const double z = tb2_wf_z<MODE>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow,   \
-                                                zs, mhz, win);                                  \
+                const double z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval,    \
+                                                     zrow, zs, mhz);                            \
                 const double u = (p < W) ? up : NEG;                                            \
                 const double ul = (p >= 1 && p - 1 < W) ? upl : NEG;                            \
                 double nx;                                                                      \
@@ -466,8 +482,7 @@ __device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_
                 xout = nx;                                                                      \
                 cw |= code << (2 * (j & 15));                                                   \
                 if ((j & 15) == 15 || j == W - 1) { tbr[j >> 4] = cw; cw = 0u; }                \
-                if (is_tail) rowbuf[j] = nx;                                                    \
-                if (want_best && nx > best) { best = nx; best_idx = j; }                        \
+                if (is_tail) tb2_rb_st<RBS>(rowbuf, rb_s, j, nx);                               \
                 if (DBG) {                                                                      \
                     pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;                                   \
                     pc.dbg_tb[(size_t)(r + 1) * W + j] = code;                                  \
@@ -478,10 +493,12 @@ __device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_
         for (; t <= t_end && t < t_lo; ++t) TB2_WF_GENERAL_STEP()
         if (t <= t_hi) {
             // ---------- steady state: no band-edge predicates, z one step ahead ----------
-            double z = tb2_wf_z<MODE>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz, win);
+            double z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz);
+            uint32_t *tbp = tbr + (j >> 4);
+            const int jd = d;
             for (; t <= t_hi; ++t) {
                 double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);
-                if (lane == 0) up = lane0_buf ? rowbuf[j + d] : 0.0;
+                if (lane == 0) up = lane0_buf ? tb2_rb_ld<RBS>(rowbuf, rb_s, j + jd) : 0.0;
                 const double upl = up_prev;
                 up_prev = up;
                 const double a = (x - stay) + z;
@@ -493,21 +510,28 @@ __device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_
                 if (cc > a) nx = cc; else code = 0u;
                 x = nx;
                 xout = nx;
-                cw |= code << (2 * (j & 15));
-                if ((j & 15) == 15) { tbr[j >> 4] = cw; cw = 0u; }
-                if (is_tail) rowbuf[j] = nx;
-                if (track && want_best && nx > best) { best = nx; best_idx = j; }
+                const int jm = j & 15;
+                cw |= code << (2 * jm);
+                if (jm == 15) { *tbp++ = cw; cw = 0u; }
+                if (is_tail) tb2_rb_st<RBS>(rowbuf, rb_s, j, nx);
                 if (DBG) {
                     pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;
                     pc.dbg_tb[(size_t)(r + 1) * W + j] = code;
                 }
                 ++j; ++ep;
-                z = tb2_wf_z<MODE>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz, win);
+                z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz);
             }
         }
         for (; t <= t_end; ++t) TB2_WF_GENERAL_STEP()
 #undef TB2_WF_GENERAL_STEP
         __syncwarp();
+    }
+    // first arg-max of the last row (it is the tail row of the last strip: rowbuf)
+    double best = NEG;
+    int best_idx = 0x7fffffff;
+    for (int jj = lane; jj < W; jj += 32) {
+        const double v = tb2_rb_ld<RBS>(rowbuf, rb_s, jj);
+        if (v > best) { best = v; best_idx = jj; }
     }
     *argmax_out = tb2_warp_argmax(best, best_idx);
     return TB2_OK;
@@ -516,24 +540,32 @@ __device__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_
 __device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode, int r_end,
                                   double *rowbuf, uint32_t *tbw, int *argmax_out)
 {
-    if (pc.dbg_fwd) {
-        if (mode == TB2_MODE_EXPLICIT)
-            return tb2_wavefront_rows_t<TB2_MODE_EXPLICIT, true>(pc, c, r_end, rowbuf, tbw, argmax_out);
-        if (mode == TB2_MODE_MASKED)
-            return tb2_wavefront_rows_t<TB2_MODE_MASKED, true>(pc, c, r_end, rowbuf, tbw, argmax_out);
-        return tb2_wavefront_rows_t<TB2_MODE_PLAIN, true>(pc, c, r_end, rowbuf, tbw, argmax_out);
+    const bool rbs = __isShared(rowbuf);
+    const bool win = c.winsor != 0;
+#define TB2_WF_CALL(M, D, WN, RB) tb2_wavefront_rows_t<M, D, WN, RB>(pc, c, r_end, rowbuf, tbw, argmax_out)
+    if (mode == TB2_MODE_EXPLICIT) {
+        // mirror API: explicit z matrix, optional full dumps
+        if (pc.dbg_fwd) return rbs ? TB2_WF_CALL(TB2_MODE_EXPLICIT, true, false, true)
+                                   : TB2_WF_CALL(TB2_MODE_EXPLICIT, true, false, false);
+        return TB2_ERR_INVALID_ARG;
     }
-    if (mode == TB2_MODE_EXPLICIT)
-        return tb2_wavefront_rows_t<TB2_MODE_EXPLICIT, false>(pc, c, r_end, rowbuf, tbw, argmax_out);
-    if (mode == TB2_MODE_MASKED)
-        return tb2_wavefront_rows_t<TB2_MODE_MASKED, false>(pc, c, r_end, rowbuf, tbw, argmax_out);
-    return tb2_wavefront_rows_t<TB2_MODE_PLAIN, false>(pc, c, r_end, rowbuf, tbw, argmax_out);
+    if (mode == TB2_MODE_MASKED) {
+        if (win) return rbs ? TB2_WF_CALL(TB2_MODE_MASKED, false, true, true)
+                            : TB2_WF_CALL(TB2_MODE_MASKED, false, true, false);
+        return rbs ? TB2_WF_CALL(TB2_MODE_MASKED, false, false, true)
+                   : TB2_WF_CALL(TB2_MODE_MASKED, false, false, false);
+    }
+    if (win) return rbs ? TB2_WF_CALL(TB2_MODE_PLAIN, false, true, true)
+                        : TB2_WF_CALL(TB2_MODE_PLAIN, false, true, false);
+    return rbs ? TB2_WF_CALL(TB2_MODE_PLAIN, false, false, true)
+               : TB2_WF_CALL(TB2_MODE_PLAIN, false, false, false);
+#undef TB2_WF_CALL
 }
 
 // traceback over rows [row_lo, row_hi) stored in the wavefront layout; cur_event is
 // carried in and out (c_banded_traceback _c_dynamic_programming.pyx:295-308).
 // Lanes prefetch three words around the expected band position of 32 rows at once.
-__device__ int tb2_tb_seg_wf(const uint32_t *tbw, int wpr, const int *starts, int row_hi,
+__device__ __noinline__ int tb2_tb_seg_wf(const uint32_t *tbw, int wpr, const int *starts, int row_hi,
                              int row_lo, int W, int thresh, int *cur_event_io, int *read_tb)
 {
     const int lane = tb2_lane();

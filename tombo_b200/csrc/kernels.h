@@ -13,6 +13,7 @@ struct AlignBatch {
     const double *em;
     const long long *ev_off;
     const int *n_cpts;        // n_cpts[r * stride]
+    const int *num_events;    // requested events (class filter), may be null
     const double *rm, *rs;
     const long long *base_off;
     int *starts, *read_tb, *segs;
@@ -29,6 +30,8 @@ struct AlignLaunchCfg {
     int smem_cells;       // per-warp row-buffer capacity in shared memory (cells)
     size_t tb_words;      // per-warp packed-move scratch (uint32 words)
     int grow_cells;       // per-warp global row scratch capacity (0 = none)
+    int klass;            // 0: all reads; 1: static-band kernel, short reads only;
+                          // 2: general kernel, long reads only
 };
 
 // launches the persistent warp-per-read kernel on ctx->stream

@@ -127,10 +127,13 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
     return TB2_OK;
 }
 
+// capacity plan per read class: short reads (static band only) get the lean kernel
 void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *raw_off, double ratio,
-                      AlignLaunchCfg *cfg)
+                      AlignLaunchCfg *cs, AlignLaunchCfg *cl, int *n_short, int *n_long)
 {
-    cfg->smem_cells = 32; cfg->tb_words = 32; cfg->grow_cells = 0;
+    cs->smem_cells = 32; cs->tb_words = 32; cs->grow_cells = 0; cs->klass = 1;
+    cl->smem_cells = 32; cl->tb_words = 32; cl->grow_cells = 0; cl->klass = 2;
+    *n_short = *n_long = 0;
     for (int r = 0; r < hb.n; ++r) {
         const long long nb = hb.base_off[r + 1] - hb.base_off[r];
         const long long n_em = num_events_of(raw_off[r + 1] - raw_off[r], nb, p, ratio) - 1;
@@ -139,26 +142,28 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
         const long long w_static = std::max<long long>(1, n_em - mask_len);
         const bool is_short = n_em < p.start_bw + p.start_n_bases || nb < p.start_n_bases;
         if (is_short) {
+            ++*n_short;
             if (tb2_row_cells(w_static) / 32 > TB2_MAX_CHUNK) continue;  // CAPACITY status on device
             // static band: one plain row (wavefront engine); smem_cells counts pairs
-            cfg->smem_cells = std::max(cfg->smem_cells, tb2_row_cells((w_static + 1) / 2));
-            cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(nb, w_static));
+            cs->smem_cells = std::max(cs->smem_cells, tb2_row_cells((w_static + 1) / 2));
+            cs->tb_words = std::max(cs->tb_words, (size_t)(nb * ((w_static + 15) / 16)));
         } else {
-            cfg->smem_cells = std::max(cfg->smem_cells,
-                                       tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2,
-                                                                         p.bandwidth)));
-            cfg->tb_words = std::max(cfg->tb_words, std::max(tb2_tb_words(nb, p.bandwidth),
-                                                             tb2_tb_words(p.start_n_bases, p.start_bw)));
+            ++*n_long;
+            cl->smem_cells = std::max(cl->smem_cells,
+                                      tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2,
+                                                                        p.bandwidth)));
+            cl->tb_words = std::max(cl->tb_words, std::max(tb2_tb_words(nb, p.bandwidth),
+                                                           tb2_tb_words(p.start_n_bases, p.start_bw)));
             if (n_em >= p.start_save_bw + p.start_n_bases) {
-                cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(p.start_n_bases, p.start_save_bw));
-                cfg->grow_cells = std::max(cfg->grow_cells, tb2_row_cells(p.start_save_bw));
+                cl->tb_words = std::max(cl->tb_words, tb2_tb_words(p.start_n_bases, p.start_save_bw));
+                cl->grow_cells = std::max(cl->grow_cells, tb2_row_cells(p.start_save_bw));
             }
             // long reads may fall back to the static band (failed start search with
             // too few events for the save bandwidth, or a start too close to the
             // read end: resquiggle.py:996-999, 1024-1027); rows live in global memory
             if (tb2_row_cells(w_static) / 32 <= TB2_MAX_CHUNK) {
-                cfg->tb_words = std::max(cfg->tb_words, tb2_tb_words(nb, w_static));
-                cfg->grow_cells = std::max(cfg->grow_cells, tb2_row_cells(w_static));
+                cl->tb_words = std::max(cl->tb_words, tb2_tb_words(nb, w_static));
+                cl->grow_cells = std::max(cl->grow_cells, tb2_row_cells(w_static));
             }
         }
     }
@@ -210,6 +215,7 @@ AlignBatch make_align_batch(tb2_ctx *ctx, const BatchView &v, const tb2_params &
     ab.starts = v.starts; ab.read_tb = v.read_tb; ab.segs = v.segs_dp;
     ab.stride = (int)(sizeof(ReadState) / sizeof(int));
     ab.n_cpts = &v.st[0].n_cpts;
+    ab.num_events = &v.st[0].num_events;
     ab.rsrtr = &v.st[0].rsrtr;
     ab.status = &v.st[0].status;
     ab.active = &v.st[0].active;
@@ -221,7 +227,8 @@ AlignBatch make_align_batch(tb2_ctx *ctx, const BatchView &v, const tb2_params &
 
 // one resquiggle_read call over the batch (all active reads)
 int run_call(tb2_ctx *ctx, const BatchView &v, const tb2_params &p, const StagePolicy &sp,
-             const AlignLaunchCfg &acfg, int first_call, double *norm_mean_dev,
+             const AlignLaunchCfg *acfg /* [2]: short, long; tb_words 0 = class empty */,
+             int first_call, double *norm_mean_dev,
              double *norm_sig_dev, size_t rawdp_cap)
 {
     int rc;
@@ -238,7 +245,10 @@ int run_call(tb2_ctx *ctx, const BatchView &v, const tb2_params &p, const StageP
     }
     if ((rc = tb2_launch_event_means(ctx, v))) return rc;
     TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
-    if ((rc = tb2_launch_align(ctx, make_align_batch(ctx, v, p, sp.sig_match_thresh), acfg))) return rc;
+    for (int k = 0; k < 2; ++k)
+        if (acfg[k].tb_words > 0 &&
+            (rc = tb2_launch_align(ctx, make_align_batch(ctx, v, p, sp.sig_match_thresh), acfg[k])))
+            return rc;
     TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
     if ((rc = tb2_launch_resolve(ctx, v, p, sp, rawdp_cap))) return rc;
     if ((rc = tb2_launch_base_means(ctx, v))) return rc;
@@ -394,8 +404,12 @@ extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (attempt == 1 && (!policy->rescue || counters[1] == 0)) break;
         const tb2_params &p = attempt == 0 ? *params : *save_params;
-        AlignLaunchCfg acfg;
-        plan_align_batch(p, hb, h->raw_off.data(), sp.min_event_to_seq_ratio, &acfg);
+        AlignLaunchCfg acfg[2];
+        int n_short = 0, n_long = 0;
+        plan_align_batch(p, hb, h->raw_off.data(), sp.min_event_to_seq_ratio, &acfg[0], &acfg[1],
+                         &n_short, &n_long);
+        if (n_short == 0) acfg[0].tb_words = 0;
+        if (n_long == 0) acfg[1].tb_words = 0;
         if ((rc = tb2_launch_start_attempt(ctx, v, attempt))) return rc;
         if (h->has_sv_in || h->has_stalls_in) {
             k_apply_inputs<<<(n + 255) / 256, 256, 0, s>>>(

@@ -716,9 +716,12 @@ __global__ void __launch_bounds__(ST_THREADS) k_base_means(BatchView b)
 #define TS_BINS 2048
 #define TS_BUF 2048
 
+#define TS_ABINS 4096   // bins of the approximate (fp32) pre-pass
+
 struct TsSmem {
     double ev[TS_MAX], md[TS_MAX];
-    unsigned int hist[TS_BINS + 2];
+    float evf[TS_MAX], mdf[TS_MAX];
+    unsigned int hist[TS_ABINS + 2];   // also holds the TS_BINS + 2 exact bins
     double buf[TS_BUF];
     unsigned int nbuf, b1, b2, below;
     int ok;
@@ -794,7 +797,109 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
     bool have = false;
     // ---- bracket from a sample of n/2 independent pairs ----
     const int hs = n / 2;
-    if (hs >= 16) {
+    // ---- fast path: fp32 pre-pass picks a bracket [L, H), then ONE exact pass counts
+    // the slopes below L and collects those inside; every decision of that pass is
+    // exact (products with an error guard, the true fp64 division whenever a pair is
+    // within the guard or inside the bracket), so the selected order statistics are
+    // the same doubles np.median sees.  If the bracket misses, fall through.
+    if (hs >= 16 && Np > 4 * TS_ABINS) {
+        auto f_samp = [&](int i) { return ts_slope(t, i, i + hs); };
+        double lo, hi, d0;
+        tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.30), false, &lo, &d0, sm);
+        tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.70), false, &hi, &d0, sm);
+        const float lo_f = (float)lo, hi_f = (float)hi;
+        const float w_f = (hi_f - lo_f) / (float)TS_ABINS;
+        if (hi_f > lo_f && w_f > 0.0f && isfinite(w_f)) {
+            const float inv_w = 1.0f / w_f;
+            for (int i = tid; i < n; i += ST_THREADS) { t.evf[i] = (float)t.ev[i]; t.mdf[i] = (float)t.md[i]; }
+            for (int i = tid; i < TS_ABINS + 2; i += ST_THREADS) t.hist[i] = 0;
+            if (tid == 0) { t.nbuf = 0; t.ok = 0; t.below = 0; t.b1 = 0; t.b2 = 0; }
+            __syncthreads();
+            ts_for_pairs(n, [&](int i, int j) {
+                const float de = t.evf[i] - t.evf[j];
+                const float sa = (de == 0.0f) ? 1000.0f : __fdividef(t.mdf[i] - t.mdf[j], de);
+                int q;
+                if (sa < lo_f) q = 0;
+                else if (!(sa < hi_f)) q = TS_ABINS + 1;
+                else q = min(TS_ABINS - 1, (int)((sa - lo_f) * inv_w)) + 1;
+                atomicAdd(&t.hist[q], 1u);
+            });
+            __syncthreads();
+            // bins holding the (approximate) ranks k1 and k1+1: 256 threads x 17 bins
+            {
+                const int per = (TS_ABINS + 2 + ST_THREADS - 1) / ST_THREADS;
+                const int q0 = min(TS_ABINS + 2, tid * per), q1 = min(TS_ABINS + 2, q0 + per);
+                unsigned int mine = 0;
+                for (int q = q0; q < q1; ++q) mine += t.hist[q];
+                const int lane = tid & 31, warp = tid >> 5;
+                unsigned int inc = mine;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned int o = __shfl_up_sync(TB2_FULL_MASK, inc, off);
+                    if (lane >= off) inc += o;
+                }
+                if (lane == 31) sm.warp_tot[warp] = inc;
+                __syncthreads();
+                unsigned int base = 0;
+                for (int q = 0; q < warp; ++q) base += sm.warp_tot[q];
+                long long cum = (long long)base + inc - mine;
+                const long long kA = k1, kB = even ? k1 + 1 : k1;
+                for (int q = q0; q < q1; ++q) {
+                    const long long c = t.hist[q];
+                    if (kA >= cum && kA < cum + c) t.b1 = q;
+                    if (kB >= cum && kB < cum + c) t.b2 = q;
+                    cum += c;
+                }
+                __syncthreads();
+            }
+            const int bA = (int)t.b1, bB = (int)t.b2;
+            if (bA >= 1 && bB <= TS_ABINS) {
+                // exact bracket with a one-bin margin on both sides
+                const double L = (double)lo_f + (double)w_f * (double)(bA - 2);
+                const double H = (double)lo_f + (double)w_f * (double)(bB + 1);
+                const double EPS = 3.5527136788005009e-15;   // 2^-48
+                __syncthreads();
+                unsigned int below = 0;
+                ts_for_pairs(n, [&](int i, int j) {
+                    const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
+                    int cls;          // -1: s < L, 0: L <= s < H, +1: s >= H
+                    double sv = 1000.0;
+                    bool have_s = (de == 0.0);
+                    if (have_s) cls = (sv < L) ? -1 : ((sv < H) ? 0 : 1);
+                    else {
+                        const double tL = L * de, tH = H * de;
+                        const double gL = fabs(tL) * EPS, gH = fabs(tH) * EPS;
+                        const bool pos = de > 0.0;
+                        const bool sure_below_L = pos ? (dm < tL - gL) : (dm > tL + gL);
+                        const bool sure_above_H = pos ? (dm > tH + gH) : (dm < tH - gH);
+                        if (sure_below_L) cls = -1;
+                        else if (sure_above_H) cls = 1;
+                        else {
+                            sv = dm / de;       // the reference's value (_c_helper.pyx:374-376)
+                            have_s = true;
+                            cls = (sv < L) ? -1 : ((sv < H) ? 0 : 1);
+                        }
+                    }
+                    if (cls < 0) ++below;
+                    else if (cls == 0) {
+                        const unsigned int slot = atomicAdd(&t.nbuf, 1u);
+                        if (slot < TS_BUF) t.buf[slot] = sv;
+                    }
+                });
+                below = tb2_block_sum(below, sm);
+                __syncthreads();
+                const long long nbuf = t.nbuf;
+                const long long kB = even ? k1 + 1 : k1;
+                if (nbuf <= TS_BUF && k1 >= (long long)below && kB < (long long)below + nbuf) {
+                    tb2_block_select2([&](int i) { return t.buf[i]; }, PredAll(), (int)nbuf,
+                                      (int)(k1 - (long long)below), even, &v1, &v2, sm);
+                    have = true;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (!have && hs >= 16) {
         auto f_samp = [&](int i) { return ts_slope(t, i, i + hs); };
         double lo, hi, d0;
         tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.30), false, &lo, &d0, sm);
