@@ -217,6 +217,9 @@ int tb2_debug_last_assignment(tb2_ctx *ctx, int64_t n_bases, int64_t *starts_out
  * pairs where the reciprocal-based division of the DP rows differs from a / b */
 int tb2_debug_div_check(tb2_ctx *ctx, uint64_t seed, int blocks, int per_thread,
                         uint64_t *mismatches, double *example4);
+/* tuning / test counters: [0] Theil-Sen calls, [1] fp32-bracket path, [2] exact
+ * histogram path, [3] generic radix-select path */
+int tb2_debug_counters(tb2_ctx *ctx, unsigned long long *out8, int reset);
 /* resolve_skipped_bases_with_raw resquiggle.py:402-540 */
 int tb2_resolve_skipped_bases_with_raw(
     tb2_ctx *ctx, const int64_t *segs, int64_t n_bases, const double *ref_means,

@@ -712,6 +712,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_base_means(BatchView b)
 // 2048-bin histogram over a sample-derived bracket narrows the median to one
 // bin, whose members are selected exactly (generic radix select as fall-back).
 // ===========================================================================
+// debug counters (tests / tuning): [0] Theil-Sen reads, [1] fast path, [2] exact
+// histogram path, [3] generic select path
+__device__ unsigned long long g_tb2_counters[8];
+
 #define TS_MAX 1000
 #define TS_BINS 2048
 #define TS_BUF 2048
@@ -723,7 +727,7 @@ struct TsSmem {
     float evf[TS_MAX], mdf[TS_MAX];
     unsigned int hist[TS_ABINS + 2];   // also holds the TS_BINS + 2 exact bins
     double buf[TS_BUF];
-    unsigned int nbuf, b1, b2, below;
+    unsigned int nbuf, b1, b2, below, maxabs_bits;
     int ok;
 };
 
@@ -791,6 +795,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
     __syncthreads();
     const long long Np = (long long)n * (n - 1) / 2;
     if (Np <= 0) { if (tid == 0) s.status = TB2_ERR_UNEXPECTED; return; }
+    if (tid == 0) atomicAdd(&g_tb2_counters[0], 1ULL);
     const bool even = (Np % 2) == 0;
     const long long k1 = even ? Np / 2 - 1 : Np / 2;   // ranks k1 (and k1+1 if even)
     double v1 = 0, v2 = 0;
@@ -811,7 +816,17 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
         const float w_f = (hi_f - lo_f) / (float)TS_ABINS;
         if (hi_f > lo_f && w_f > 0.0f && isfinite(w_f)) {
             const float inv_w = 1.0f / w_f;
-            for (int i = tid; i < n; i += ST_THREADS) { t.evf[i] = (float)t.ev[i]; t.mdf[i] = (float)t.md[i]; }
+            if (tid == 0) t.maxabs_bits = 0u;
+            __syncthreads();
+            {
+                float mx = 0.0f;
+                for (int i = tid; i < n; i += ST_THREADS) {
+                    t.evf[i] = (float)t.ev[i]; t.mdf[i] = (float)t.md[i];
+                    mx = fmaxf(mx, fmaxf(fabsf(t.evf[i]), fabsf(t.mdf[i])));
+                }
+                if (!(mx < 3.0e38f)) mx = 3.0e38f;          // inf / nan: everything is screened out
+                atomicMax(&t.maxabs_bits, __float_as_uint(mx));
+            }
             for (int i = tid; i < TS_ABINS + 2; i += ST_THREADS) t.hist[i] = 0;
             if (tid == 0) { t.nbuf = 0; t.ok = 0; t.below = 0; t.b1 = 0; t.b2 = 0; }
             __syncthreads();
@@ -857,28 +872,33 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                 // exact bracket with a one-bin margin on both sides
                 const double L = (double)lo_f + (double)w_f * (double)(bA - 2);
                 const double H = (double)lo_f + (double)w_f * (double)(bB + 1);
-                const double EPS = 3.5527136788005009e-15;   // 2^-48
+                // fp32 screen: with |values| <= M the float images carry an absolute
+                // error <= 1.3e-7 * M each, so E = dm - T*de is known to within
+                // g(T) = 1e-5 * M * (1 + |T|); outside that guard the side of T is
+                // certain, inside it the pair takes the exact fp64 path.
+                const float M = fmaxf(1.0f, __uint_as_float(t.maxabs_bits));
+                const float Lf = (float)L, Hf = (float)H;
+                const float gLf = 1e-5f * M * (1.0f + fabsf(Lf)), gHf = 1e-5f * M * (1.0f + fabsf(Hf));
                 __syncthreads();
                 unsigned int below = 0;
                 ts_for_pairs(n, [&](int i, int j) {
-                    const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
-                    int cls;          // -1: s < L, 0: L <= s < H, +1: s >= H
+                    int cls = 2;      // -1: s < L, 0: L <= s < H, +1: s >= H, 2: undecided
                     double sv = 1000.0;
-                    bool have_s = (de == 0.0);
-                    if (have_s) cls = (sv < L) ? -1 : ((sv < H) ? 0 : 1);
-                    else {
-                        const double tL = L * de, tH = H * de;
-                        const double gL = fabs(tL) * EPS, gH = fabs(tH) * EPS;
-                        const bool pos = de > 0.0;
-                        const bool sure_below_L = pos ? (dm < tL - gL) : (dm > tL + gL);
-                        const bool sure_above_H = pos ? (dm > tH + gH) : (dm < tH - gH);
-                        if (sure_below_L) cls = -1;
-                        else if (sure_above_H) cls = 1;
-                        else {
-                            sv = dm / de;       // the reference's value (_c_helper.pyx:374-376)
-                            have_s = true;
-                            cls = (sv < L) ? -1 : ((sv < H) ? 0 : 1);
+                    {
+                        const float def = t.evf[i] - t.evf[j], dmf = t.mdf[i] - t.mdf[j];
+                        if (fabsf(def) > 1e-3f * M) {
+                            const float eL = dmf - Lf * def, eH = dmf - Hf * def;
+                            const bool pos = def > 0.0f;
+                            // s < L  <=>  (dm - L*de) has the sign opposite to de
+                            if (pos ? (eL < -gLf) : (eL > gLf)) cls = -1;
+                            else if (pos ? (eH > gHf) : (eH < -gHf)) cls = 1;
                         }
+                    }
+                    if (cls == 2) {
+                        const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
+                        // the reference's value (_c_helper.pyx:371-376)
+                        sv = (de == 0.0) ? 1000.0 : dm / de;
+                        cls = (sv < L) ? -1 : ((sv < H) ? 0 : 1);
                     }
                     if (cls < 0) ++below;
                     else if (cls == 0) {
@@ -894,6 +914,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                     tb2_block_select2([&](int i) { return t.buf[i]; }, PredAll(), (int)nbuf,
                                       (int)(k1 - (long long)below), even, &v1, &v2, sm);
                     have = true;
+                    if (tid == 0) atomicAdd(&g_tb2_counters[1], 1ULL);
                 }
             }
             __syncthreads();
@@ -950,10 +971,12 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                 tb2_block_select2([&](int i) { return t.buf[i]; }, PredAll(), nbuf,
                                   (int)(k1 - (long long)t.below), even, &v1, &v2, sm);
                 have = true;
+                if (tid == 0) atomicAdd(&g_tb2_counters[2], 1ULL);
             }
         }
     }
     if (!have) {
+        if (tid == 0) { atomicAdd(&g_tb2_counters[3], 1ULL); }
         // generic exact fall-back: radix select over all pairs
         auto f_all = [&](int q) { int i, j; ts_pair_of(q, n, &i, &j); return ts_slope(t, i, j); };
         tb2_block_select2(f_all, PredAll(), (int)Np, (int)k1, even, &v1, &v2, sm);
@@ -1136,5 +1159,19 @@ int tb2_launch_finalize(tb2_ctx *ctx, const BatchView &b, const StagePolicy &pol
     k_finalize<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b, pol, first_call, norm_mean_out,
                                                           norm_signal_out);
     TB2_CHECK_LAUNCH(ctx);
+    return TB2_OK;
+}
+
+extern "C" int tb2_debug_counters(tb2_ctx *ctx, unsigned long long *out8, int reset)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!out8) return TB2_ERR_INVALID_ARG;
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    TB2_CUDA_TRY(ctx, cudaMemcpyFromSymbol(out8, g_tb2_counters, 64));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        TB2_CUDA_TRY(ctx, cudaMemcpyToSymbol(g_tb2_counters, z, 64));
+    }
     return TB2_OK;
 }
