@@ -75,7 +75,13 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
         for (int i = tid; i < n; i += TB2_SEL_THREADS) {
             if (!pred(i)) continue;
             const unsigned long long key = tb2_key(f(i));
-            if ((key & mask) == prefix) atomicAdd(&sm.hist[(unsigned int)(key >> shift) & 255u], 1u);
+            if ((key & mask) == prefix) {
+                // warp-aggregated: the leading digits of real signals are almost all
+                // equal, one atomic per distinct digit instead of one per lane
+                const unsigned int dg = (unsigned int)(key >> shift) & 255u;
+                const unsigned int peers = __match_any_sync(__activemask(), dg);
+                if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&sm.hist[dg], __popc(peers));
+            }
         }
         __syncthreads();
         // inclusive scan of the 256 bins (thread t <-> bin t)

@@ -830,15 +830,17 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             for (int i = tid; i < TS_ABINS + 2; i += ST_THREADS) t.hist[i] = 0;
             if (tid == 0) { t.nbuf = 0; t.ok = 0; t.below = 0; t.b1 = 0; t.b2 = 0; }
             __syncthreads();
+            unsigned int n_under = 0, n_over = 0;   // 60 % of the pairs: counted in registers
             ts_for_pairs(n, [&](int i, int j) {
                 const float de = t.evf[i] - t.evf[j];
                 const float sa = (de == 0.0f) ? 1000.0f : __fdividef(t.mdf[i] - t.mdf[j], de);
-                int q;
-                if (sa < lo_f) q = 0;
-                else if (!(sa < hi_f)) q = TS_ABINS + 1;
-                else q = min(TS_ABINS - 1, (int)((sa - lo_f) * inv_w)) + 1;
-                atomicAdd(&t.hist[q], 1u);
+                if (sa < lo_f) ++n_under;
+                else if (!(sa < hi_f)) ++n_over;
+                else atomicAdd(&t.hist[min(TS_ABINS - 1, (int)((sa - lo_f) * inv_w)) + 1], 1u);
             });
+            n_under = tb2_block_sum(n_under, sm);
+            n_over = tb2_block_sum(n_over, sm);
+            if (tid == 0) { t.hist[0] = n_under; t.hist[TS_ABINS + 1] = n_over; }
             __syncthreads();
             // bins holding the (approximate) ranks k1 and k1+1: 256 threads x 17 bins
             {
