@@ -129,3 +129,29 @@ def test_batch_long_reads_subsample(ctx, orc, dna_model, RPcls):
     rp, sp = RPcls(aln), RPcls(aln, save=True)
     reads = syn.make_reads(kmer_ref, cpos, 3, 1400, seed0=8000)
     _compare(ctx, orc, reads, means, sds, 6, cpos, rp, sp, seed=99)
+
+
+def test_large_batch_pipelined_chunks_match_single_chunk(ctx, dna_model, RPcls):
+    """tb2_resquiggle_batch splits big batches into chunks over two lanes (H2D of the
+    next chunk overlaps compute); results must equal the unchunked staged path"""
+    from tombo_b200 import _lib, synthetic as syn
+    import bench
+    kmer_ref, cpos = dna_model
+    means, sds = syn.kmer_table(kmer_ref)
+    ctx.set_model(means, sds, 6, cpos)
+    n = 4 * 148 * 24 * 2 + 1234           # > 1.5 chunks on a 148-SM part
+    raw, raw_off, codes, seq_off = syn.make_read_batch(kmer_ref, n, 60, 77)
+    # a few long reads so that the keyed sub-sampling (global read index) is exercised
+    rp, sp = RPcls(bench.ALN_DNA), RPcls(bench.ALN_DNA, save=True)
+    pol = _lib.make_policy('DNA', subsample_seed=5)
+    a = ctx.resquiggle_batch(raw, raw_off, codes, seq_off, rp, sp, pol)
+    a = {k: v.copy() for k, v in a.items()}
+    ctx.batch_upload(raw, raw_off, codes, seq_off, rp, pol)
+    ctx.batch_compute(rp, sp, pol)
+    b = ctx.batch_download()
+    for k in ('segs', 'read_start_rel_to_raw', 'status', 'n_iters', 'flags'):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a['scale_values'][:, :4], b['scale_values'][:, :4], equal_nan=True)
+    assert np.array_equal(a['sig_match_score'], b['sig_match_score'], equal_nan=True)
+    assert np.array_equal(a['norm_mean'], b['norm_mean'], equal_nan=True)
+    assert (a['status'] == 0).mean() > 0.9

@@ -42,6 +42,8 @@ extern "C" void tb2_ctx_destroy(tb2_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (tb2_ctx *ln : ctx->lanes) tb2_ctx_destroy(ln);
+    ctx->lanes.clear();
     for (auto &b : ctx->pool) b.release();
     ctx->model_means.release(); ctx->model_sds.release(); ctx->alt_means.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

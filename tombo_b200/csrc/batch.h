@@ -65,6 +65,7 @@ struct StagePolicy {
     double const_scale;          // NaN = None
     unsigned int subsample_seed;
     int literal_key;             // mirror API: subsample_seed already is the key
+    int read_index_base;         // index of the batch's first read in the caller's batch
 };
 
 // launch wrappers (stage_kernels.cu); all enqueue on ctx->stream

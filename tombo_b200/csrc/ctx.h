@@ -25,9 +25,10 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    bool owned = true;   // false: alias of another context's buffer (pipeline lanes)
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr; cap = 0;
     }
     template <class T> T *as() { return (T *)p; }
@@ -42,6 +43,11 @@ struct tb2_ctx {
     int64_t launches = 0;
     double last_ms_total = 0, last_ms_dp = 0, last_dp_launches = 0, last_dp_reads = 0;
     std::shared_ptr<void> batch;   // BatchHolder (pipeline.cu)
+    // tb2_resquiggle_batch pipelines large batches over two lanes (child contexts with
+    // their own stream and pools): H2D of chunk k+1 overlaps the kernels of chunk k
+    std::vector<tb2_ctx *> lanes;
+    bool async_mode = false;       // upload / download do not synchronise
+    int read_index_base = 0;       // first read of the chunk within the caller's batch
     // model tables
     DevBuf model_means, model_sds, alt_means;
     int kmer_width = 0, central_pos = 0, alt_kmer_width = 0;

@@ -203,6 +203,7 @@ StagePolicy stage_policy(const tb2_policy &pl)
     sp.const_scale = pl.const_scale;
     sp.subsample_seed = pl.subsample_seed;
     sp.literal_key = 0;
+    sp.read_index_base = 0;
     return sp;
 }
 
@@ -325,7 +326,7 @@ extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, 
     TB2_CUDA_TRY(ctx, P[B_RAWIN].reserve((size_t)h->hb.total_s * esz + 8));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_RAWIN].p, raw, (size_t)h->hb.total_s * esz, cudaMemcpyHostToDevice, s));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_SEQ].p, seq, (size_t)h->hb.total_seq, cudaMemcpyHostToDevice, s));
-    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (!ctx->async_mode) TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     h->uploaded = true;
     h->has_sv_in = h->has_stalls_in = false;
     return TB2_OK;
@@ -380,7 +381,8 @@ extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
     BatchHolder *h = holder_of(ctx);
     if (!h->uploaded) { ctx->err = "tb2_batch_upload has not been called"; return TB2_ERR_INVALID_ARG; }
     h->computed = false;
-    const StagePolicy sp = stage_policy(*policy);
+    StagePolicy sp = stage_policy(*policy);
+    sp.read_index_base = ctx->read_index_base;
     const HostBatch &hb = h->hb;
     const BatchView &v = h->v;
     const int n = hb.n;
@@ -494,7 +496,7 @@ extern "C" int tb2_batch_download(tb2_ctx *ctx, int64_t *segs, int64_t *read_sta
         TB2_CUDA_TRY(ctx, cudaMemcpyAsync(norm_mean, P[B_OUT_NORMMEAN].p, (size_t)hb.total_b * 8, cudaMemcpyDeviceToHost, s));
     if (norm_signal)
         TB2_CUDA_TRY(ctx, cudaMemcpyAsync(norm_signal, P[B_OUT_NORMSIG].p, (size_t)hb.total_s * 8, cudaMemcpyDeviceToHost, s));
-    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (!ctx->async_mode) TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return TB2_OK;
 }
 
@@ -508,11 +510,90 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
                                     int32_t *n_iters, int32_t *flags)
 {
     if (n_reads == 0) return tb2_use(ctx);
-    int rc = tb2_batch_upload(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy);
+    int rc = tb2_use(ctx);
     if (rc) return rc;
-    if ((rc = tb2_batch_compute(ctx, params, save_params, policy, norm_signal != nullptr))) return rc;
-    return tb2_batch_download(ctx, segs, read_start_rel_to_raw, scale_out, sig_match_score,
-                              norm_mean, norm_signal, status, n_iters, flags);
+    if (!raw_off || !seq_off || !params || !policy || !raw || !seq || !segs ||
+        !read_start_rel_to_raw || !scale_out || !sig_match_score || !status || !n_iters || !flags ||
+        (raw_dtype != 0 && raw_dtype != 1) || n_reads > 0x7ffffff0)
+        return TB2_ERR_INVALID_ARG;
+    // chunk = 4 reads per resident DP warp of the lean kernel
+    const int64_t CH = (int64_t)4 * ctx->sm_count * 24;
+    if (n_reads <= CH + CH / 2) {
+        rc = tb2_batch_upload(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy);
+        if (rc) return rc;
+        if ((rc = tb2_batch_compute(ctx, params, save_params, policy, norm_signal != nullptr))) return rc;
+        return tb2_batch_download(ctx, segs, read_start_rel_to_raw, scale_out, sig_match_score,
+                                  norm_mean, norm_signal, status, n_iters, flags);
+    }
+    // ---- pipelined: chunk k+1 is uploaded (pinned host memory -> async DMA) while the
+    // kernels of chunk k run; results stream back on the chunk's own stream ----
+    while (ctx->lanes.size() < 2) {
+        tb2_ctx *ln = new tb2_ctx();
+        ln->device = ctx->device; ln->sm_count = ctx->sm_count;
+        if (cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&ln->ev0) != cudaSuccess || cudaEventCreate(&ln->ev1) != cudaSuccess ||
+            cudaEventCreate(&ln->ev2) != cudaSuccess || cudaEventCreate(&ln->ev3) != cudaSuccess) {
+            delete ln;
+            ctx->err = "cannot create pipeline lane";
+            return TB2_ERR_CUDA;
+        }
+        ctx->lanes.push_back(ln);
+    }
+    for (tb2_ctx *ln : ctx->lanes) {
+        ln->model_means.p = ctx->model_means.p; ln->model_means.cap = ctx->model_means.cap;
+        ln->model_sds.p = ctx->model_sds.p; ln->model_sds.cap = ctx->model_sds.cap;
+        ln->model_means.owned = ln->model_sds.owned = false;
+        ln->kmer_width = ctx->kmer_width; ln->central_pos = ctx->central_pos;
+        ln->async_mode = true;
+    }
+    const int K = ctx->kmer_width;
+    const int n = (int)n_reads;
+    const int n_chunks = (int)((n_reads + CH - 1) / CH);
+    std::vector<int64_t> base_off((size_t)n + 1, 0);
+    for (int r = 0; r < n; ++r)
+        base_off[r + 1] = base_off[r] + std::max<int64_t>(0, (seq_off[r + 1] - seq_off[r]) - (K - 1));
+    std::vector<std::vector<int64_t>> ro((size_t)n_chunks), so((size_t)n_chunks);
+    const size_t esz = raw_dtype == 0 ? 8 : 2;
+    auto bounds = [&](int k, int *a, int *b) {
+        *a = (int)((int64_t)n * k / n_chunks);
+        *b = (int)((int64_t)n * (k + 1) / n_chunks);
+    };
+    auto upload = [&](int k) -> int {
+        int a, b;
+        bounds(k, &a, &b);
+        tb2_ctx *ln = ctx->lanes[k & 1];
+        if (cudaStreamSynchronize(ln->stream) != cudaSuccess) return TB2_ERR_CUDA;  // lane free again
+        ro[k].resize((size_t)(b - a) + 1);
+        so[k].resize((size_t)(b - a) + 1);
+        for (int r = a; r <= b; ++r) { ro[k][r - a] = raw_off[r] - raw_off[a]; so[k][r - a] = seq_off[r] - seq_off[a]; }
+        return tb2_batch_upload(ln, b - a, (const char *)raw + (size_t)raw_off[a] * esz, raw_dtype,
+                                ro[k].data(), seq + seq_off[a], so[k].data(), params, policy);
+    };
+    double ms_total = 0, ms_dp = 0, dp_launches = 0, dp_reads = 0;
+    rc = upload(0);
+    for (int k = 0; k < n_chunks && rc == TB2_OK; ++k) {
+        int a, b;
+        bounds(k, &a, &b);
+        tb2_ctx *ln = ctx->lanes[k & 1];
+        if (k + 1 < n_chunks && (rc = upload(k + 1))) break;
+        ln->read_index_base = a;
+        if ((rc = tb2_batch_compute(ln, params, save_params, policy, norm_signal != nullptr))) break;
+        ms_total += ln->last_ms_total; ms_dp += ln->last_ms_dp;
+        dp_launches += ln->last_dp_launches; dp_reads += ln->last_dp_reads;
+        rc = tb2_batch_download(ln, segs + base_off[a] + a, read_start_rel_to_raw + a, scale_out + a,
+                                sig_match_score + a, norm_mean ? norm_mean + base_off[a] : nullptr,
+                                norm_signal ? norm_signal + raw_off[a] : nullptr, status + a,
+                                n_iters + a, flags + a);
+    }
+    for (tb2_ctx *ln : ctx->lanes) {
+        if (cudaStreamSynchronize(ln->stream) != cudaSuccess && rc == TB2_OK) rc = TB2_ERR_CUDA;
+        ctx->launches += ln->launches;
+        ln->launches = 0;
+        if (rc != TB2_OK && ctx->err.empty()) ctx->err = ln->err;
+    }
+    ctx->last_ms_total = ms_total; ctx->last_ms_dp = ms_dp;
+    ctx->last_dp_launches = dp_launches; ctx->last_dp_reads = dp_reads;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

@@ -784,7 +784,8 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
         n = TS_MAX;
         const unsigned int key = pol.literal_key
             ? pol.subsample_seed
-            : tb2_subsample_key(pol.subsample_seed, (unsigned int)r, (unsigned int)s.calls);
+            : tb2_subsample_key(pol.subsample_seed, (unsigned int)(r + pol.read_index_base),
+                                (unsigned int)s.calls);
         for (int i = tid; i < n; i += ST_THREADS) {
             const int k = tb2_perm_index(i, nb, key);
             t.ev[i] = bm[k]; t.md[i] = rm[k];
