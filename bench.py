@@ -113,14 +113,20 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------
 # synthetic workload
 # ---------------------------------------------------------------------------
-def make_workload(n_reads, seed, pinned_factory=None):
+ALN_MIXED = (4.2, 4.2, 400, 1500, 20.0, 40, 750, 2500, 250)   # configs[2]: bandwidth = 400
+
+
+def make_workload(n_reads, seed, pinned_factory=None, mixed=False):
     from tombo_b200 import synthetic as syn
     kmer_ref, cpos = syn.make_kmer_ref('DNA', 0)
     chunks, offs, seqs, soffs = [], [0], [], [0]
     done, ci = 0, 0
     while done < n_reads:
         m = min(10000, n_reads - done)
-        raw, ro, codes, so = syn.make_read_batch(kmer_ref, m, N_BASES, seed * 1000 + ci)
+        nbs = N_BASES
+        if mixed:   # configs[2]: 2k-20k raw samples per read
+            nbs = np.random.RandomState(seed * 7919 + ci).randint(222, 2223, m)
+        raw, ro, codes, so = syn.make_read_batch(kmer_ref, m, nbs, seed * 1000 + ci)
         chunks.append(raw); seqs.append(codes)
         offs.extend((ro[1:] + offs[-1]).tolist())
         soffs.extend((so[1:] + soffs[-1]).tolist())
@@ -150,7 +156,9 @@ def dp_algorithmic_bytes(raw_off, seq_off, k, rp):
     n_em = e - 1
     mask = np.minimum(b, n_em) // 4
     w = n_em - mask
-    cells = b * w
+    short = (n_em < rp.start_bw + rp.start_n_bases) | (b < rp.start_n_bases)
+    # long reads: start search (start_n_bases x start_bw) + one band row per base
+    cells = np.where(short, b * w, rp.start_n_bases * rp.start_bw + b * rp.bandwidth)
     a = 8 * e + 16 * b + 8 * b + 8 * (b + 1) + (2 * cells + 7) // 8
     return a.astype(np.float64), cells.astype(np.float64)
 
@@ -273,6 +281,8 @@ def main():
     ap.add_argument('--reads', type=int, default=100000, help='reads per GPU per step')
     ap.add_argument('--cpu-sample', type=int, default=0, help='reads of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='c1', choices=['c1', 'mixed'],
+                    help='c1: BASELINE configs[1] (default); mixed: configs[2]-like lengths')
     args = ap.parse_args()
     rank, world, local, dist = dist_setup(args.gpus)
     cores = host_cores()
@@ -318,10 +328,15 @@ def main():
         pa = _lib.PinnedArray((n,), dt)
         pinned.append(pa)
         return pa.array
-    kmer_ref, cpos, raw, raw_off, seq, seq_off = make_workload(args.reads, 1 + rank, pin)
+    mixed = args.workload == 'mixed'
+    kmer_ref, cpos, raw, raw_off, seq, seq_off = make_workload(args.reads, 1 + rank, pin, mixed)
     means, sds = syn.kmer_table(kmer_ref)
     ctx.set_model(means, sds, 6, cpos)
-    rp, sp = RP(), RP(save=True)
+    aln = ALN_MIXED if mixed else ALN_DNA
+    rp, sp = RP(aln), RP(aln, save=True)
+    if mixed:
+        workload = ('configs[2]-like: %d synthetic DNA reads/GPU, 2k-20k samples (222-2222 bases), '
+                    'bandwidth=400 adaptive band + save-bandwidth rescue, float64 raw' % args.reads)
     pol = _lib.make_policy('DNA', subsample_seed=rank)
     n_reads = raw_off.shape[0] - 1
     n_samples = int(raw_off[-1])
@@ -413,7 +428,7 @@ def main():
             'gpu_launches': int(launches_timed),
             'clocks': clocks,
         }
-        if args.gpus == 1 and not args.no_cpu_baseline:
+        if args.gpus == 1 and not args.no_cpu_baseline and not mixed:
             kind = cpu_baseline_kind()
             n = args.cpu_sample or cores * 48
             cb = run_cpu(n, cores, kind)

@@ -149,6 +149,114 @@ __device__ __forceinline__ int tb2_warp_argmax(double best, int best_idx)
 }
 
 // ---------------------------------------------------------------------------
+// Fast row for band widths <= 512 (chunk <= 16 cells per lane, one move word) with
+// both row buffers in shared memory -- the adaptive band of real reads (bandwidth
+// 200-500).  Same arithmetic as tb2_dp_row; the z-scores and the best
+// diag/skip candidate of every cell stay in registers, so the re-walks that fix the
+// speculation cost one add and one compare per cell instead of a division and two
+// shared-memory reads.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double tb2_lds(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void tb2_sts(unsigned a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v));
+}
+
+__device__ __forceinline__ void tb2_dp_row16(const double *prev, double *cur, int W, int chunk,
+                                             int lane, const RowSpec &rs, const DpConsts &c, int d,
+                                             bool first_skip, uint32_t &codeword, double &best,
+                                             int &best_idx)
+{
+    const double NEG = tb2_neg_inf();
+    const unsigned prev_s = (unsigned)__cvta_generic_to_shared(prev);
+    const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cur) + 8u * (unsigned)lane;
+    const double stay = c.stay_pen, skip = c.skip_pen;
+    const int j0 = lane * chunk;
+    const int nvalid = max(0, min(chunk, W - j0));
+    double z[16], cc[16];
+    uint32_t cfw = 0u, cw = 0u;
+    int p = j0 + d;
+    int lane_p = p / chunk;
+    int i_p = p - lane_p * chunk;
+    double pm1 = NEG;
+    if (p >= 1 && p - 1 < W) {
+        const int q = p - 1, lq = q / chunk;
+        pm1 = tb2_lds(prev_s + 8u * (unsigned)((q - lq * chunk) * 32 + lq));
+    }
+    double x = NEG;
+    best = NEG;
+    best_idx = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        z[i] = 0.0; cc[i] = NEG;
+        if (i < nvalid) {
+            const int j = j0 + i;
+            const double zz = tb2_zscore(rs, c, j);
+            const double pv = (p < W) ? tb2_lds(prev_s + 8u * (unsigned)(i_p * 32 + lane_p)) : NEG;
+            double cand = pm1 + zz;               // diag (code 2)
+            uint32_t cf = 2u;
+            const double sk = pv - skip;          // skip (code 1)
+            double a;
+            if (j == 0) {
+                // band position 0: skip if the band did not move, else diag; no stay
+                a = NEG;
+                if (first_skip) { cand = sk; cf = 1u; }
+            } else {
+                if (sk > cand) { cand = sk; cf = 1u; }
+                a = (x - stay) + zz;              // stay (code 0)
+            }
+            double nx = a;
+            uint32_t code = 0u;
+            if (cand > a) { nx = cand; code = cf; }
+            z[i] = zz; cc[i] = cand;
+            cfw |= cf << (2 * i);
+            cw |= code << (2 * i);
+            tb2_sts(cur_s + 256u * (unsigned)i, nx);
+            if (nx > best) { best = nx; best_idx = j; }
+            x = nx;
+            pm1 = pv;
+            ++p;
+            if (++i_p == chunk) { i_p = 0; ++lane_p; }
+        }
+    }
+    double x_end = x;
+    double last_in = NEG;
+    for (;;) {
+        const double xin = __shfl_up_sync(TB2_FULL_MASK, x_end, 1);
+        const bool need = (lane > 0) && (nvalid > 0) && (xin != last_in);
+        if (!__any_sync(TB2_FULL_MASK, need)) break;
+        if (need) {
+            double xx = xin;
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (i < nvalid && !done) {
+                    const double a = (xx - stay) + z[i];
+                    double nx = a;
+                    uint32_t code = 0u;
+                    if (cc[i] > a) { nx = cc[i]; code = (cfw >> (2 * i)) & 3u; }
+                    const double old = tb2_lds(cur_s + 256u * (unsigned)i);
+                    cw = (cw & ~(3u << (2 * i))) | (code << (2 * i));
+                    if (nx == old) done = true;
+                    else tb2_sts(cur_s + 256u * (unsigned)i, nx);
+                    const int j = j0 + i;
+                    if (nx > best || (nx == best && j < best_idx)) { best = nx; best_idx = j; }
+                    xx = nx;
+                }
+            }
+            if (!done) x_end = xx;
+            last_in = xin;
+        }
+    }
+    codeword = cw;
+}
+
+// ---------------------------------------------------------------------------
 // Pass description: a run of consecutive rows sharing one band width.
 // ---------------------------------------------------------------------------
 enum { TB2_MODE_PLAIN = 0, TB2_MODE_MASKED = 1, TB2_MODE_ADAPTIVE = 2, TB2_MODE_EXPLICIT = 3 };
@@ -191,6 +299,7 @@ __device__ __noinline__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, i
     double *prev = (*cur_sel) ? pc.buf1 : pc.buf0;
     double *cur = (*cur_sel) ? pc.buf0 : pc.buf1;
     int last_argmax = *argmax_out;
+    const bool rows_in_smem = __isShared(pc.buf0);
     int prev_start = (r_begin > 0) ? pc.starts[r_begin - 1] : 0;
     const int half_bw = W / 2;
     for (int r = r_begin; r < r_end; ++r) {
@@ -233,7 +342,10 @@ __device__ __noinline__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, i
         const bool first_skip = (r == 0) || (d == 0);
         uint32_t codes[WPL];
         double best; int best_idx;
-        tb2_dp_row<WPL>(prev, cur, W, chunk, lane, rs, c, d, first_skip, codes, best, best_idx);
+        if (WPL == 1 && rows_in_smem)
+            tb2_dp_row16(prev, cur, W, chunk, lane, rs, c, d, first_skip, codes[0], best, best_idx);
+        else
+            tb2_dp_row<WPL>(prev, cur, W, chunk, lane, rs, c, d, first_skip, codes, best, best_idx);
 #pragma unroll
         for (int w = 0; w < WPL; ++w)
             pc.tb[(size_t)r * (WPL * 32) + w * 32 + lane] = codes[w];
