@@ -44,9 +44,11 @@ __device__ __forceinline__ bool tb2_setup_geom(PassCtx &pc, const WarpRes &wr, i
     pc.W = W;
     pc.chunk = (W + 31) / 32;
     const int cells = pc.chunk * 32;
+    pc.zbuf = nullptr; pc.cbuf = nullptr;
     if (2 * cells <= wr.smem_cap) {
         pc.buf0 = wr.smem_rows;
         pc.buf1 = wr.smem_rows + cells;
+        if (4 * cells <= wr.smem_cap) { pc.zbuf = wr.smem_rows + 2 * cells; pc.cbuf = wr.smem_rows + 3 * cells; }
         return true;
     }
     if (wr.grow != nullptr && cells <= wr.grow_cap) {
@@ -111,7 +113,7 @@ __device__ __forceinline__ void tb2_pc_defaults(PassCtx &pc, const AlignRead &a,
     pc.mask_fill = TB2_MASK_FILL_Z_SCORE;
     pc.mask_shifted = (TB2_MASK_FILL_Z_SCORE - c.z_shift) + c.z_shift;  // resquiggle.py:666,678
     pc.starts = a.starts; pc.tb = wr.tb; pc.dbg_fwd = nullptr; pc.dbg_tb = nullptr;
-    pc.buf0 = nullptr; pc.buf1 = nullptr; pc.chunk = 0; pc.W = 0;
+    pc.buf0 = nullptr; pc.buf1 = nullptr; pc.zbuf = nullptr; pc.cbuf = nullptr; pc.chunk = 0; pc.W = 0;
 }
 
 // static-band forward pass + traceback over rows [0, n_rows) (wavefront engine)

@@ -12,7 +12,7 @@
 // (find_adaptive_base_assignment resquiggle.py:986-989): wavefront engine only, so
 // fewer registers and twice the resident warps of the general kernel.
 template <int KLASS>
-__global__ void __launch_bounds__(ALIGN_WARPS * 32, (KLASS == 1) ? 6 : 1)
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, (KLASS == 1) ? 6 : 4)
 k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, int *counter)
 {
     extern __shared__ double smem[];
@@ -122,6 +122,7 @@ __global__ void k_banded_forward_dbg(const double *z, const long long *starts64,
     pc.em = nullptr; pc.n_em = 0; pc.rm = nullptr; pc.rs_ = nullptr; pc.zmat = z;
     pc.mso = 0; pc.msp_start = 0; pc.msp_stop = 0; pc.mask_fill = 0; pc.mask_shifted = 0;
     pc.starts = starts32; pc.tb = tbp; pc.dbg_fwd = fwd; pc.dbg_tb = tb64;
+    pc.zbuf = nullptr; pc.cbuf = nullptr;
     int st = TB2_OK;
     pc.W = W; pc.chunk = (W + 31) / 32; pc.buf0 = nullptr; pc.buf1 = nullptr;
     double *rowbuf = tb2_wf_rowbuf(wr, W);
@@ -155,6 +156,7 @@ __global__ void k_adaptive_dbg(double *fwd, long long *tb64, long long *starts64
     pc.em = em; pc.n_em = n_em; pc.rm = rm; pc.rs_ = rs; pc.zmat = nullptr;
     pc.mso = 0; pc.msp_start = 0; pc.msp_stop = 0; pc.mask_fill = mask_fill; pc.mask_shifted = 0;
     pc.starts = starts32; pc.tb = tbp; pc.dbg_fwd = fwd; pc.dbg_tb = tb64;
+    pc.zbuf = nullptr; pc.cbuf = nullptr;
     int st = TB2_OK;
     if (!tb2_setup_geom(pc, wr, W)) st = TB2_ERR_CAPACITY;
     const int wpl = tb2_wpl_of(pc.chunk);
@@ -564,4 +566,18 @@ extern "C" int tb2_find_seq_start_in_events(tb2_ctx *ctx, const double *event_me
     return run_single(ctx, 1, event_means, n_events, ref_means, ref_sds, n_ref, params, num_bases,
                       num_events, check_score, sig_match_thresh, nullptr, 0, start_loc,
                       events_per_base, read_status);
+}
+
+extern "C" int tb2_debug_dp_counters(tb2_ctx *ctx, unsigned long long *out8, int reset)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!out8) return TB2_ERR_INVALID_ARG;
+    TB2_CUDA_TRY(ctx, cudaDeviceSynchronize());
+    TB2_CUDA_TRY(ctx, cudaMemcpyFromSymbol(out8, g_tb2_dp_counters, 64));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        TB2_CUDA_TRY(ctx, cudaMemcpyToSymbol(g_tb2_dp_counters, z, 64));
+    }
+    return TB2_OK;
 }

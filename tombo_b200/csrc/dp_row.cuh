@@ -156,6 +156,10 @@ __device__ __forceinline__ int tb2_warp_argmax(double best, int best_idx)
 // speculation cost one add and one compare per cell instead of a division and two
 // shared-memory reads.
 // ---------------------------------------------------------------------------
+// tuning counters of the lane-chunk engine: [0] rows, [1] fix-up rounds, [2] cells
+// re-walked, [3] rows that needed more than 2 rounds
+__device__ unsigned long long g_tb2_dp_counters[8];
+
 __device__ __forceinline__ double tb2_lds(unsigned a)
 {
     double v;
@@ -167,18 +171,20 @@ __device__ __forceinline__ void tb2_sts(unsigned a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v));
 }
 
-__device__ __forceinline__ void tb2_dp_row16(const double *prev, double *cur, int W, int chunk,
-                                             int lane, const RowSpec &rs, const DpConsts &c, int d,
+// prev_s / cur_s / z_s / c_s: shared-memory byte addresses of four lane-transposed
+// row buffers (previous row, current row, z-scores, best diag/skip candidate)
+__device__ __forceinline__ void tb2_dp_row_s(unsigned prev_s, unsigned cur_s, unsigned z_s,
+                                             unsigned c_s, int W, int chunk, int lane,
+                                             const RowSpec &rs, const DpConsts &c, int d,
                                              bool first_skip, uint32_t &codeword, double &best,
                                              int &best_idx)
 {
     const double NEG = tb2_neg_inf();
-    const unsigned prev_s = (unsigned)__cvta_generic_to_shared(prev);
-    const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cur) + 8u * (unsigned)lane;
     const double stay = c.stay_pen, skip = c.skip_pen;
     const int j0 = lane * chunk;
     const int nvalid = max(0, min(chunk, W - j0));
-    double z[16], cc[16];
+    const unsigned lo8 = 8u * (unsigned)lane;
+    cur_s += lo8; z_s += lo8; c_s += lo8;
     uint32_t cfw = 0u, cw = 0u;
     int p = j0 + d;
     int lane_p = p / chunk;
@@ -191,69 +197,78 @@ __device__ __forceinline__ void tb2_dp_row16(const double *prev, double *cur, in
     double x = NEG;
     best = NEG;
     best_idx = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        z[i] = 0.0; cc[i] = NEG;
-        if (i < nvalid) {
-            const int j = j0 + i;
-            const double zz = tb2_zscore(rs, c, j);
-            const double pv = (p < W) ? tb2_lds(prev_s + 8u * (unsigned)(i_p * 32 + lane_p)) : NEG;
-            double cand = pm1 + zz;               // diag (code 2)
-            uint32_t cf = 2u;
-            const double sk = pv - skip;          // skip (code 1)
-            double a;
-            if (j == 0) {
-                // band position 0: skip if the band did not move, else diag; no stay
-                a = NEG;
-                if (first_skip) { cand = sk; cf = 1u; }
-            } else {
-                if (sk > cand) { cand = sk; cf = 1u; }
-                a = (x - stay) + zz;              // stay (code 0)
-            }
-            double nx = a;
-            uint32_t code = 0u;
-            if (cand > a) { nx = cand; code = cf; }
-            z[i] = zz; cc[i] = cand;
-            cfw |= cf << (2 * i);
-            cw |= code << (2 * i);
-            tb2_sts(cur_s + 256u * (unsigned)i, nx);
-            if (nx > best) { best = nx; best_idx = j; }
-            x = nx;
-            pm1 = pv;
-            ++p;
-            if (++i_p == chunk) { i_p = 0; ++lane_p; }
+#pragma unroll 1
+    for (int i = 0; i < nvalid; ++i) {
+        const int j = j0 + i;
+        const double zz = tb2_zscore(rs, c, j);
+        const double pv = (p < W) ? tb2_lds(prev_s + 8u * (unsigned)(i_p * 32 + lane_p)) : NEG;
+        double cand = pm1 + zz;               // diag (code 2)
+        uint32_t cf = 2u;
+        const double sk = pv - skip;          // skip (code 1)
+        double a;
+        if (j == 0) {
+            // band position 0: skip if the band did not move, else diag; no stay
+            a = NEG;
+            if (first_skip) { cand = sk; cf = 1u; }
+        } else {
+            if (sk > cand) { cand = sk; cf = 1u; }
+            a = (x - stay) + zz;              // stay (code 0)
         }
+        double nx = a;
+        uint32_t code = 0u;
+        if (cand > a) { nx = cand; code = cf; }
+        const unsigned off = 256u * (unsigned)i;
+        tb2_sts(z_s + off, zz);
+        tb2_sts(c_s + off, cand);
+        tb2_sts(cur_s + off, nx);
+        cfw |= cf << (2 * i);
+        cw |= code << (2 * i);
+        if (nx > best) { best = nx; best_idx = j; }
+        x = nx;
+        pm1 = pv;
+        ++p;
+        if (++i_p == chunk) { i_p = 0; ++lane_p; }
     }
     double x_end = x;
     double last_in = NEG;
+    int n_rounds = 0, n_walked = 0;
     for (;;) {
         const double xin = __shfl_up_sync(TB2_FULL_MASK, x_end, 1);
         const bool need = (lane > 0) && (nvalid > 0) && (xin != last_in);
         if (!__any_sync(TB2_FULL_MASK, need)) break;
+        ++n_rounds;
         if (need) {
             double xx = xin;
             bool done = false;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (i < nvalid && !done) {
-                    const double a = (xx - stay) + z[i];
-                    double nx = a;
-                    uint32_t code = 0u;
-                    if (cc[i] > a) { nx = cc[i]; code = (cfw >> (2 * i)) & 3u; }
-                    const double old = tb2_lds(cur_s + 256u * (unsigned)i);
-                    cw = (cw & ~(3u << (2 * i))) | (code << (2 * i));
-                    if (nx == old) done = true;
-                    else tb2_sts(cur_s + 256u * (unsigned)i, nx);
-                    const int j = j0 + i;
-                    if (nx > best || (nx == best && j < best_idx)) { best = nx; best_idx = j; }
-                    xx = nx;
-                }
+#pragma unroll 1
+            for (int i = 0; i < nvalid; ++i) {
+                ++n_walked;
+                const unsigned off = 256u * (unsigned)i;
+                const double a = (xx - stay) + tb2_lds(z_s + off);
+                const double cand = tb2_lds(c_s + off);
+                double nx = a;
+                uint32_t code = 0u;
+                if (cand > a) { nx = cand; code = (cfw >> (2 * i)) & 3u; }
+                const double old = tb2_lds(cur_s + off);
+                cw = (cw & ~(3u << (2 * i))) | (code << (2 * i));
+                const int j = j0 + i;
+                if (nx > best || (nx == best && j < best_idx)) { best = nx; best_idx = j; }
+                xx = nx;
+                if (nx == old) { done = true; break; }
+                tb2_sts(cur_s + off, nx);
             }
             if (!done) x_end = xx;
             last_in = xin;
         }
     }
     codeword = cw;
+    n_walked = __reduce_add_sync(TB2_FULL_MASK, n_walked);
+    if (lane == 0) {
+        atomicAdd(&g_tb2_dp_counters[0], 1ULL);
+        atomicAdd(&g_tb2_dp_counters[1], (unsigned long long)n_rounds);
+        atomicAdd(&g_tb2_dp_counters[2], (unsigned long long)n_walked);
+        if (n_rounds > 2) atomicAdd(&g_tb2_dp_counters[3], 1ULL);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -266,6 +281,7 @@ struct PassCtx {
     int W, chunk;
     // row buffers (lane-transposed, >= chunk*32 doubles each)
     double *buf0, *buf1;
+    double *zbuf, *cbuf;     // optional: z-score / candidate rows (fast adaptive path)
     // inputs
     const double *em;   // event means (already offset by events_start_clip)
     int n_em;
@@ -299,7 +315,10 @@ __device__ __noinline__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, i
     double *prev = (*cur_sel) ? pc.buf1 : pc.buf0;
     double *cur = (*cur_sel) ? pc.buf0 : pc.buf1;
     int last_argmax = *argmax_out;
-    const bool rows_in_smem = __isShared(pc.buf0);
+    // fast path: four row buffers in shared memory (rows, z-scores, candidates)
+    const bool fast_s = (pc.zbuf != nullptr) && __isShared(pc.buf0);
+    const unsigned z_s = fast_s ? (unsigned)__cvta_generic_to_shared(pc.zbuf) : 0u;
+    const unsigned c_s = fast_s ? (unsigned)__cvta_generic_to_shared(pc.cbuf) : 0u;
     int prev_start = (r_begin > 0) ? pc.starts[r_begin - 1] : 0;
     const int half_bw = W / 2;
     for (int r = r_begin; r < r_end; ++r) {
@@ -342,8 +361,9 @@ __device__ __noinline__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, i
         const bool first_skip = (r == 0) || (d == 0);
         uint32_t codes[WPL];
         double best; int best_idx;
-        if (WPL == 1 && rows_in_smem)
-            tb2_dp_row16(prev, cur, W, chunk, lane, rs, c, d, first_skip, codes[0], best, best_idx);
+        if (WPL == 1 && fast_s)
+            tb2_dp_row_s((unsigned)__cvta_generic_to_shared(prev), (unsigned)__cvta_generic_to_shared(cur),
+                         z_s, c_s, W, chunk, lane, rs, c, d, first_skip, codes[0], best, best_idx);
         else
             tb2_dp_row<WPL>(prev, cur, W, chunk, lane, rs, c, d, first_skip, codes, best, best_idx);
 #pragma unroll

@@ -149,9 +149,12 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
             cs->tb_words = std::max(cs->tb_words, (size_t)(nb * ((w_static + 15) / 16)));
         } else {
             ++*n_long;
+            // start search: one plain row; adaptive rows: four transposed rows when the
+            // band is narrow enough for the fast path (<= 512 cells), else two
+            const long long bw_cells = tb2_row_cells(p.bandwidth);
             cl->smem_cells = std::max(cl->smem_cells,
                                       tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2,
-                                                                        p.bandwidth)));
+                                                                        p.bandwidth <= 512 ? 2 * bw_cells : bw_cells)));
             cl->tb_words = std::max(cl->tb_words, std::max(tb2_tb_words(nb, p.bandwidth),
                                                            tb2_tb_words(p.start_n_bases, p.start_bw)));
             if (n_em >= p.start_save_bw + p.start_n_bases) {
