@@ -262,6 +262,7 @@ __device__ __forceinline__ void tb2_dp_row_s(unsigned prev_s, unsigned cur_s, un
         }
     }
     codeword = cw;
+#ifdef TB2_DP_COUNTERS   // tuning build only: four contended global atomics per row
     n_walked = __reduce_add_sync(TB2_FULL_MASK, n_walked);
     if (lane == 0) {
         atomicAdd(&g_tb2_dp_counters[0], 1ULL);
@@ -269,6 +270,9 @@ __device__ __forceinline__ void tb2_dp_row_s(unsigned prev_s, unsigned cur_s, un
         atomicAdd(&g_tb2_dp_counters[2], (unsigned long long)n_walked);
         if (n_rounds > 2) atomicAdd(&g_tb2_dp_counters[3], 1ULL);
     }
+#else
+    (void)n_rounds; (void)n_walked;
+#endif
 }
 
 // ---------------------------------------------------------------------------
