@@ -123,14 +123,15 @@ __device__ int tb2_static_pass(PassCtx &pc, const WarpRes &wr, const DpConsts &c
     pc.W = W;
     double *rowbuf = tb2_wf_rowbuf(wr, W);
     if (rowbuf == nullptr) return TB2_ERR_CAPACITY;
-    const int wpr = tb2_wf_wpr(W);
-    if ((size_t)n_rows * wpr > wr.tb_words) return TB2_ERR_CAPACITY;
+    const long long words = tb2_wf_total_words(pc.starts, n_rows, W);
+    if (words < 0) return TB2_ERR_UNEXPECTED;
+    if ((size_t)words > wr.tb_words) return TB2_ERR_CAPACITY;
     int amax = 0;
     int st = tb2_wavefront_rows(pc, c, TB2_MODE_PLAIN, n_rows, rowbuf, wr.tb, &amax);
     if (st != TB2_OK) return st;
     int cur_event = amax + pc.starts[n_rows - 1];
     if (tb2_lane() == 0) read_tb[n_rows] = cur_event + 1;
-    return tb2_tb_seg_wf(wr.tb, wpr, pc.starts, n_rows, 0, W, -1, &cur_event, read_tb);
+    return tb2_tb_seg_wf(wr.tb, words, pc.starts, n_rows, W, -1, &cur_event, read_tb);
 }
 
 // find_seq_start_in_events resquiggle.py:685-752
@@ -260,7 +261,6 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     pc.em = a.em + clip; pc.n_em = n_emc; pc.mso = mso;
     if (!tb2_setup_geom(pc, wr, bw)) return TB2_ERR_CAPACITY;
     const int wpl = tb2_wpl_of(pc.chunk);
-    const int wpr = tb2_wf_wpr(bw);
     if (wpl > TB2_MAX_WPL) return TB2_ERR_CAPACITY;
     const int bes0 = (half_bw <= mso) ? 0 : mso - half_bw;
     const int t2 = (int)((double)(half_bw + 1) / epb);
@@ -281,7 +281,9 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     if (mask_seq_len > tmp_len) mask_seq_len = tmp_len;
     if (mask_seq_len > nb) return TB2_ERR_UNEXPECTED;
     // move scratch: wavefront rows first, then the lane-chunk rows (indexed by row)
-    const size_t wf_words = (size_t)mask_seq_len * wpr;
+    const long long wf_words_ll = tb2_wf_total_words(a.starts, mask_seq_len, bw);
+    if (wf_words_ll < 0) return TB2_ERR_UNEXPECTED;
+    const size_t wf_words = (size_t)wf_words_ll;
     if (wf_words + (size_t)nb * wpl * 32 > wr.tb_words) return TB2_ERR_CAPACITY;
     uint32_t *tb_wf = wr.tb, *tb_chunk = wr.tb + wf_words;
     pc.tb = tb_chunk;
@@ -324,7 +326,7 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     st = tb2_tb_seg_chunk_dyn(wpl, tb_chunk, a.starts, nb, mask_seq_len, bw, pc.chunk, thresh,
                               &cur_event, a.read_tb);
     if (st != TB2_OK) return st;
-    st = tb2_tb_seg_wf(tb_wf, wpr, a.starts, mask_seq_len, 0, bw, thresh, &cur_event, a.read_tb);
+    st = tb2_tb_seg_wf(tb_wf, wf_words_ll, a.starts, mask_seq_len, bw, thresh, &cur_event, a.read_tb);
     if (st != TB2_OK) return st;
     // _trim_traceback :754-764
     if (lane == 0) {

@@ -126,7 +126,7 @@ __global__ void k_banded_forward_dbg(const double *z, const long long *starts64,
     int st = TB2_OK;
     pc.W = W; pc.chunk = (W + 31) / 32; pc.buf0 = nullptr; pc.buf1 = nullptr;
     double *rowbuf = tb2_wf_rowbuf(wr, W);
-    if (rowbuf == nullptr || (size_t)nb * tb2_wf_wpr(W) > wr.tb_words) st = TB2_ERR_CAPACITY;
+    if (rowbuf == nullptr) st = TB2_ERR_CAPACITY;
     if (st == TB2_OK) {
         for (int r = lane; r < nb; r += 32) starts32[r] = (int)starts64[r];
         for (int j = lane; j < W; j += 32) { fwd[j] = 0.0; tb64[j] = 0; }
@@ -360,14 +360,14 @@ static void plan_align(const tb2_params &p, long long n_em, long long nb, int *s
     const bool is_short = n_em < p.start_bw + p.start_n_bases || nb < p.start_n_bases;
     long long w_main = is_short ? w_static : std::max<long long>(p.start_bw, p.bandwidth);
     *smem_cells = std::max(*smem_cells, tb2_row_cells(w_main));
-    size_t tw = is_short ? tb2_tb_words(nb, w_static)
-                         : std::max(tb2_tb_words(nb, p.bandwidth),
-                                    tb2_tb_words(p.start_n_bases, p.start_bw));
+    size_t tw = is_short ? tb2_tb_words(nb, w_static, mask_len + 1)
+                         : std::max(tb2_tb_words(nb, p.bandwidth, n_em + p.bandwidth),
+                                    tb2_tb_words(p.start_n_bases, p.start_bw, p.start_n_bases));
     if (!is_short) {
         // rare fall-backs keep their rows in global memory
         long long w_rare = p.start_save_bw;
         if (n_em >= p.start_save_bw + p.start_n_bases)
-            tw = std::max(tw, tb2_tb_words(p.start_n_bases, p.start_save_bw));
+            tw = std::max(tw, tb2_tb_words(p.start_n_bases, p.start_save_bw, p.start_n_bases));
         *grow_cells = std::max(*grow_cells, tb2_row_cells(w_rare));
     }
     *tb_words = std::max(*tb_words, tw);
@@ -430,7 +430,7 @@ extern "C" int tb2_find_adaptive_base_assignment(
     AlignLaunchCfg cfg = {32, 32, 0, 0};
     plan_align(*params, n_em, nb, &cfg.smem_cells, &cfg.tb_words, &cfg.grow_cells);
     // the single-read mirror also covers the rare static fall-back of long reads
-    cfg.tb_words = std::max(cfg.tb_words, tb2_tb_words(nb, std::max<long long>(1, n_em - std::min(nb, n_em) / 4)));
+    cfg.tb_words = std::max(cfg.tb_words, tb2_tb_words(nb, std::max<long long>(1, n_em - std::min(nb, n_em) / 4), n_em));
     cfg.grow_cells = std::max(cfg.grow_cells, tb2_row_cells(std::max<long long>(1, n_em)));
     rc = tb2_launch_align(ctx, b, cfg);
     if (rc) return rc;
@@ -508,7 +508,7 @@ static int run_single(tb2_ctx *ctx, int mode, const double *em, int64_t n_em, co
     if (W < 1 || rows < 1) return TB2_ERR_INVALID_ARG;
     if (tb2_row_cells(W) / 32 > TB2_MAX_CHUNK) { if (read_status) *read_status = TB2_ERR_CAPACITY; return TB2_OK; }
     const DbgGeom g = dbg_geom(W);
-    const size_t tbw = tb2_tb_words(rows, W);
+    const size_t tbw = tb2_tb_words(rows, W, n_em);
     TB2_CUDA_TRY(ctx, P[S_A].reserve((size_t)n_em * 8));
     TB2_CUDA_TRY(ctx, P[S_B].reserve((size_t)nb * 8));
     TB2_CUDA_TRY(ctx, P[S_C].reserve((size_t)nb * 8));

@@ -492,9 +492,34 @@ __device__ __noinline__ int tb2_tb_seg_chunk(const uint32_t *tb, const int *star
 // construction.  Strips are chained through one row buffer in shared memory
 // (writes of the strip's last row trail the reads of its first row by >= 31
 // cells).  Event means are read coalesced (32 consecutive events per step).
-// Moves: 2 bits/cell, row-major u32 words  tb[row * wpr + (j >> 4)].
+//
+// Moves: 2 bits/cell packed in STEP space: word (strip, k, lane) holds lane's moves
+// of steps t_begin + 16k .. +15 at  tb[strip_base + k * 32 + lane]  -- every 16
+// steps the warp stores one coalesced 128-byte line, and a traceback path crossing
+// a strip touches a handful of lines.  Strip sizes follow from the band starts
+// (tb2_wf_strip_words), so forward pass and traceback agree without a table.
 // ===========================================================================
-__device__ __forceinline__ int tb2_wf_wpr(int W) { return (W + 15) >> 4; }
+__device__ __forceinline__ int tb2_wf_strip_words(const int *starts, int s0, int r_end, int W)
+{
+    const int last = min(31, r_end - 1 - s0);
+    const int span = starts[s0 + last] - starts[s0] + W - 1 + last;   // t_end - t_begin
+    return span < 0 ? -1 : ((span >> 4) + 1) * 32;
+}
+
+// total packed-move words of a wavefront pass over rows [0, r_end); -1 for band
+// starts that move left by more than the strip skew can follow
+__device__ long long tb2_wf_total_words(const int *starts, int r_end, int W)
+{
+    long long sum = 0;
+    int bad = 0;
+    for (int s0 = tb2_lane() * 32; s0 < r_end; s0 += 32 * 32) {
+        const int w = tb2_wf_strip_words(starts, s0, r_end, W);
+        if (w < 0) bad = 1; else sum += w;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(TB2_FULL_MASK, sum, off);
+    return __any_sync(TB2_FULL_MASK, bad) ? -1 : sum;
+}
 
 // shifted z-score of one cell for the wavefront engine.  The divide is the exact
 // reciprocal form (tb2_div_by): inv_sd = RN(1 / sd) once per row.
@@ -528,17 +553,49 @@ __device__ __forceinline__ void tb2_rb_st(double *rb, unsigned rb_s, int i, doub
     else rb[i] = v;
 }
 
+// one steady-state step (U = position inside the 16-step group): lane 0 takes the
+// cell above from the row buffer (predicated load at a running address), the tail
+// lane stores its result there; moves enter the word by a funnel shift.
+#define TB2_WF_FAST_STEP(U)                                                                     \
+    {                                                                                           \
+        double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);                                     \
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.f64 %0, [%1+%3]; }"    \
+                     : "+d"(up) : "r"(rd_a), "r"(l0flag), "n"(8 * (U)));                        \
+        const double zn = tb2_wf_z<MODE, WIN>(ep + (U) + 1, j + (U) + 1, mu, sd, inv_sd, lo,    \
+                                              hi, maskval, nullptr, zs, mhz);                   \
+        const double a = (x - stay) + z;                                                        \
+        double cc = up_prev + z;                                                                \
+        uint32_t code = 2u;                                                                     \
+        const double sk = up - skip;                                                            \
+        if (sk > cc) { cc = sk; code = 1u; }                                                    \
+        double nx = a;                                                                          \
+        if (cc > a) nx = cc; else code = 0u;                                                    \
+        up_prev = up;                                                                           \
+        x = nx; xout = nx; z = zn;                                                              \
+        cw = __funnelshift_r(cw, code, 2);                                                      \
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0+%3], %1; }"    \
+                     :: "r"(wr_a), "d"(nx), "r"(tlflag), "n"(8 * (U)) : "memory");              \
+    }
+
 template <int MODE, bool DBG, bool WIN, bool RBS>
 __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpConsts &c, int r_end,
                                                  double *rowbuf, uint32_t *tbw, int *argmax_out)
 {
     const int lane = tb2_lane();
-    const int W = pc.W, wpr = tb2_wf_wpr(W);
+    const int W = pc.W;
     const double NEG = tb2_neg_inf();
     const double stay = c.stay_pen, skip = c.skip_pen, zs = c.z_shift, mhz = c.mhz;
     const unsigned rb_s = RBS ? (unsigned)__cvta_generic_to_shared(rowbuf) : 0u;
     const double *em = pc.em;
     const int *starts = pc.starts;
+    // the steady state is only built for the production modes with the row buffer in
+    // shared memory; its first strip reads "the row above row 0" as zeros
+    constexpr bool FAST = RBS && !DBG && MODE != TB2_MODE_EXPLICIT;
+    if (FAST) {
+        for (int jj = lane; jj < W; jj += 32) tb2_rb_st<RBS>(rowbuf, rb_s, jj, 0.0);
+        __syncwarp();
+    }
+    uint32_t *tbs = tbw;
     for (int s0 = 0; s0 < r_end; s0 += 32) {
         const int r = s0 + lane;
         const bool row_ok = r < r_end;
@@ -562,8 +619,6 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
         const double *zrow = (MODE == TB2_MODE_EXPLICIT && row_ok) ? pc.zmat + (size_t)r * W : nullptr;
         const bool first_skip = (r == 0) || (d == 0);
         const bool is_tail = row_ok && (lane == lane_last);       // feeds the next strip
-        const bool lane0_buf = (lane == 0) && (s0 > 0);
-        uint32_t *tbr = tbw + (size_t)(row_ok ? r : 0) * wpr;
         // uniform time bounds of the strip
         const int start_first = __shfl_sync(TB2_FULL_MASK, start, 0);
         const int start_last = __shfl_sync(TB2_FULL_MASK, start, lane_last);
@@ -575,7 +630,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
         // steady state: every lane of a full strip is inside its band with j >= 1 and
         // both cells of the row above available
         int t_lo = start_last + lane_last + 1, t_hi = start_first + W - 2 - dmax;
-        if (lane_last != 31) { t_lo = t_end + 1; t_hi = t_end; }   // partial strip: general path
+        if (!FAST || lane_last != 31) { t_lo = t_end + 1; t_hi = t_end; }   // general path only
         double x = 0.0, xout = 0.0, up_prev = 0.0;
         uint32_t cw = 0u;
         int j = t_begin - lane - start;
@@ -595,6 +650,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
                 }                                                                               \
             }                                                                                   \
             up_prev = up;                                                                       \
+            const int tq = (t - t_begin) & 15;                                                  \
             if (row_ok && j >= 0 && j < W) {                                                    \
                 const double z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval,    \
                                                      zrow, zs, mhz);                            \
@@ -616,50 +672,43 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
                 }                                                                               \
                 x = nx;                                                                         \
                 xout = nx;                                                                      \
-                cw |= code << (2 * (j & 15));                                                   \
-                if ((j & 15) == 15 || j == W - 1) { tbr[j >> 4] = cw; cw = 0u; }                \
+                cw |= code << (2 * tq);                                                         \
                 if (is_tail) tb2_rb_st<RBS>(rowbuf, rb_s, j, nx);                               \
                 if (DBG) {                                                                      \
                     pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;                                   \
                     pc.dbg_tb[(size_t)(r + 1) * W + j] = code;                                  \
                 }                                                                               \
             }                                                                                   \
+            if (!DBG && (tq == 15 || t == t_end)) {                                             \
+                tbs[((t - t_begin) >> 4) * 32 + lane] = cw;                                     \
+                cw = 0u;                                                                        \
+            }                                                                                   \
             ++j; ++ep;                                                                          \
         }
-        for (; t <= t_end && t < t_lo; ++t) TB2_WF_GENERAL_STEP()
-        if (t <= t_hi) {
-            // ---------- steady state: no band-edge predicates, z one step ahead ----------
-            double z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz);
-            uint32_t *tbp = tbr + (j >> 4);
-            const int jd = d;
-            for (; t <= t_hi; ++t) {
-                double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);
-                if (lane == 0) up = lane0_buf ? tb2_rb_ld<RBS>(rowbuf, rb_s, j + jd) : 0.0;
-                const double upl = up_prev;
-                up_prev = up;
-                const double a = (x - stay) + z;
-                double cc = upl + z;
-                uint32_t code = 2u;
-                const double sk = up - skip;
-                if (sk > cc) { cc = sk; code = 1u; }
-                double nx = a;
-                if (cc > a) nx = cc; else code = 0u;
-                x = nx;
-                xout = nx;
-                const int jm = j & 15;
-                cw |= code << (2 * jm);
-                if (jm == 15) { *tbp++ = cw; cw = 0u; }
-                if (is_tail) tb2_rb_st<RBS>(rowbuf, rb_s, j, nx);
-                if (DBG) {
-                    pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;
-                    pc.dbg_tb[(size_t)(r + 1) * W + j] = code;
-                }
-                ++j; ++ep;
-                z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval, zrow, zs, mhz);
+        for (; t <= t_end && (t < t_lo || ((t - t_begin) & 15) != 0); ++t) TB2_WF_GENERAL_STEP()
+        if (FAST && t + 15 <= t_hi) {
+            // ---------- steady state: groups of 16 steps, no band-edge predicates, z one
+            // step ahead, one coalesced move-word store per group ----------
+            double z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval, nullptr, zs, mhz);
+            unsigned rd_a = rb_s + 8u * (unsigned)(j + d);     // lane 0: cell above
+            unsigned wr_a = rb_s + 8u * (unsigned)j;           // tail lane: own cell
+            const unsigned l0flag = lane == 0, tlflag = is_tail;
+            uint32_t *tbp = tbs + ((t - t_begin) >> 4) * 32 + lane;
+            for (; t + 15 <= t_hi; t += 16) {
+                TB2_WF_FAST_STEP(0) TB2_WF_FAST_STEP(1) TB2_WF_FAST_STEP(2) TB2_WF_FAST_STEP(3)
+                TB2_WF_FAST_STEP(4) TB2_WF_FAST_STEP(5) TB2_WF_FAST_STEP(6) TB2_WF_FAST_STEP(7)
+                TB2_WF_FAST_STEP(8) TB2_WF_FAST_STEP(9) TB2_WF_FAST_STEP(10) TB2_WF_FAST_STEP(11)
+                TB2_WF_FAST_STEP(12) TB2_WF_FAST_STEP(13) TB2_WF_FAST_STEP(14) TB2_WF_FAST_STEP(15)
+                *tbp = cw;
+                tbp += 32;
+                rd_a += 128u; wr_a += 128u;
+                j += 16; ep += 16;
             }
+            cw = 0u;
         }
         for (; t <= t_end; ++t) TB2_WF_GENERAL_STEP()
 #undef TB2_WF_GENERAL_STEP
+        tbs += (((t_end - t_begin) >> 4) + 1) * 32;
         __syncwarp();
     }
     // first arg-max of the last row (it is the tail row of the last strip: rowbuf)
@@ -672,6 +721,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
     *argmax_out = tb2_warp_argmax(best, best_idx);
     return TB2_OK;
 }
+#undef TB2_WF_FAST_STEP
 
 __device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode, int r_end,
                                   double *rowbuf, uint32_t *tbw, int *argmax_out)
@@ -698,45 +748,56 @@ __device__ int tb2_wavefront_rows(const PassCtx &pc, const DpConsts &c, int mode
 #undef TB2_WF_CALL
 }
 
-// traceback over rows [row_lo, row_hi) stored in the wavefront layout; cur_event is
-// carried in and out (c_banded_traceback _c_dynamic_programming.pyx:295-308).
-// Lanes prefetch three words around the expected band position of 32 rows at once.
-__device__ __noinline__ int tb2_tb_seg_wf(const uint32_t *tbw, int wpr, const int *starts, int row_hi,
-                             int row_lo, int W, int thresh, int *cur_event_io, int *read_tb)
+// traceback over rows [0, n_rows) stored in the wavefront layout (total_words =
+// tb2_wf_total_words of the pass); cur_event is carried in and out
+// (c_banded_traceback _c_dynamic_programming.pyx:295-308).  Strip by strip from the
+// top: lanes prefetch three step-words around the expected position of their row.
+__device__ __noinline__ int tb2_tb_seg_wf(const uint32_t *tbw, long long total_words, const int *starts,
+                             int n_rows, int W, int thresh, int *cur_event_io, int *read_tb)
 {
     const int lane = tb2_lane();
     int cur_event = *cur_event_io;
-    while (row_hi > row_lo) {
-        const int nblk = min(32, row_hi - row_lo);
-        const int my_row = row_hi - 1 - lane;
+    const uint32_t *tbs = tbw + total_words;
+    for (int s0 = ((n_rows - 1) >> 5) << 5; s0 >= 0; s0 -= 32) {
+        const int nblk = min(32, n_rows - s0);
+        const int sw = tb2_wf_strip_words(starts, s0, n_rows, W);
+        if (sw < 0) return TB2_ERR_UNEXPECTED;
+        tbs -= sw;
+        const int nw = sw >> 5;
+        const int t_begin = starts[s0];
+        // lane L holds row s0 + L; the path is expected to keep its average slope down
+        // to the first row
+        const float slope = (float)(cur_event - starts[0]) / (float)(s0 + nblk);
         int my_start = 0, base = 0;
         uint32_t w0 = 0, w1 = 0, w2 = 0;
         if (lane < nblk) {
-            my_start = starts[my_row];
-            const int est = cur_event - lane - my_start;
-            base = min(max((est >> 4) - 1, 0), max(wpr - 3, 0));
-            const uint32_t *rw = tbw + (size_t)my_row * wpr;
-            w0 = rw[base];
-            if (base + 1 < wpr) w1 = rw[base + 1];
-            if (base + 2 < wpr) w2 = rw[base + 2];
+            my_start = starts[s0 + lane];
+            const int est = cur_event - (int)((float)(nblk - 1 - lane) * slope) + lane - t_begin;
+            base = min(max((est >> 4) - 1, 0), max(nw - 3, 0));
+            const uint32_t *rw = tbs + lane;
+            w0 = rw[base * 32];
+            if (base + 1 < nw) w1 = rw[(base + 1) * 32];
+            if (base + 2 < nw) w2 = rw[(base + 2) * 32];
         }
-        for (int k = 0; k < nblk; ++k) {
-            const int row = row_hi - 1 - k;
+        for (int k = nblk - 1; k >= 0; --k) {
+            const int row = s0 + k;
             const int st = __shfl_sync(TB2_FULL_MASK, my_start, k);
             const int bs = __shfl_sync(TB2_FULL_MASK, base, k);
             int bp = cur_event - st;
             if (bp < 0 || bp >= W) return TB2_ERR_UNEXPECTED;
+            const int toff = st + k - t_begin;      // step = bp + toff
             uint32_t code;
             for (;;) {
-                const int wi = bp >> 4, rel = wi - bs;
+                const int ts = bp + toff;
+                const int wi = ts >> 4, rel = wi - bs;
                 uint32_t v;
                 if (rel >= 0 && rel < 3) {
                     const uint32_t mine = rel == 0 ? w0 : (rel == 1 ? w1 : w2);
                     v = __shfl_sync(TB2_FULL_MASK, mine, k);
                 } else {
-                    v = tbw[(size_t)row * wpr + wi];
+                    v = tbs[wi * 32 + k];
                 }
-                code = (v >> (2 * (bp & 15))) & 3u;
+                code = (v >> (2 * (ts & 15))) & 3u;
                 if (code != 0u) break;
                 --bp;
                 if (bp < 0) return TB2_ERR_UNEXPECTED;
@@ -746,7 +807,6 @@ __device__ __noinline__ int tb2_tb_seg_wf(const uint32_t *tbw, int wpr, const in
             cur_event = st + bp;
             if (lane == 0) read_tb[row] = cur_event + 1;
         }
-        row_hi -= nblk;
     }
     *cur_event_io = cur_event;
     __syncwarp();

@@ -39,13 +39,20 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
 
 // capacity helper (host): packed-move words needed for (rows, W)
 #define TB2_MAX_CHUNK 256   // cells per lane: band widths up to 8192 (dp_align.cuh)
-static inline size_t tb2_tb_words(long long rows, long long W)
+// wavefront engine: step-space move words, 32 * (strip span / 16 + 1) per 32-row strip
+// (dp_row.cuh tb2_wf_strip_words); drift = upper bound of last band start - first
+static inline size_t tb2_wf_words_bound(long long rows, long long W, long long drift)
+{
+    const long long strips = (rows + 31) / 32;
+    return (size_t)(strips * 32 * ((W + 30) / 16 + 2) + 2 * (drift < 0 ? 0 : drift) + 64);
+}
+static inline size_t tb2_tb_words(long long rows, long long W, long long drift)
 {
     long long chunk = (W + 31) / 32;
     long long wpl = (chunk + 15) / 16;
     wpl = wpl <= 5 ? wpl : (wpl <= 8 ? 8 : 16);   // instantiated widths (tb2_wpl_of)
-    // lane-chunk rows (wpl * 32 words) plus wavefront rows (ceil(W/16) words): an
-    // upper bound valid for every mix of the two engines
-    return (size_t)(rows * wpl * 32 + rows * ((W + 15) / 16));
+    // lane-chunk rows (wpl * 32 words) plus wavefront rows: an upper bound valid for
+    // every mix of the two engines
+    return (size_t)(rows * wpl * 32) + tb2_wf_words_bound(rows, W, drift);
 }
 static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }

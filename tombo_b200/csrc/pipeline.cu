@@ -146,7 +146,7 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
             if (tb2_row_cells(w_static) / 32 > TB2_MAX_CHUNK) continue;  // CAPACITY status on device
             // static band: one plain row (wavefront engine); smem_cells counts pairs
             cs->smem_cells = std::max(cs->smem_cells, tb2_row_cells((w_static + 1) / 2));
-            cs->tb_words = std::max(cs->tb_words, (size_t)(nb * ((w_static + 15) / 16)));
+            cs->tb_words = std::max(cs->tb_words, tb2_wf_words_bound(nb, w_static, mask_len + 1));
         } else {
             ++*n_long;
             // start search: one plain row; adaptive rows: four transposed rows when the
@@ -155,17 +155,17 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
             cl->smem_cells = std::max(cl->smem_cells,
                                       tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2,
                                                                         p.bandwidth <= 512 ? 2 * bw_cells : bw_cells)));
-            cl->tb_words = std::max(cl->tb_words, std::max(tb2_tb_words(nb, p.bandwidth),
-                                                           tb2_tb_words(p.start_n_bases, p.start_bw)));
+            cl->tb_words = std::max(cl->tb_words, std::max(tb2_tb_words(nb, p.bandwidth, n_em + p.bandwidth),
+                                                           tb2_tb_words(p.start_n_bases, p.start_bw, p.start_n_bases)));
             if (n_em >= p.start_save_bw + p.start_n_bases) {
-                cl->tb_words = std::max(cl->tb_words, tb2_tb_words(p.start_n_bases, p.start_save_bw));
+                cl->tb_words = std::max(cl->tb_words, tb2_tb_words(p.start_n_bases, p.start_save_bw, p.start_n_bases));
                 cl->grow_cells = std::max(cl->grow_cells, tb2_row_cells(p.start_save_bw));
             }
             // long reads may fall back to the static band (failed start search with
             // too few events for the save bandwidth, or a start too close to the
             // read end: resquiggle.py:996-999, 1024-1027); rows live in global memory
             if (tb2_row_cells(w_static) / 32 <= TB2_MAX_CHUNK) {
-                cl->tb_words = std::max(cl->tb_words, tb2_tb_words(nb, w_static));
+                cl->tb_words = std::max(cl->tb_words, tb2_tb_words(nb, w_static, mask_len + 1));
                 cl->grow_cells = std::max(cl->grow_cells, tb2_row_cells(w_static));
             }
         }
