@@ -600,11 +600,14 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
         const int r = s0 + lane;
         const bool row_ok = r < r_end;
         const int lane_last = min(31, r_end - 1 - s0);
-        const int start = row_ok ? starts[r] : 0;
-        const int prev_start = (row_ok && r > 0) ? starts[r - 1] : start;
+        // lanes past the last row of a partial strip mirror that row (inactive in the
+        // predicated steps, harmless passengers in the steady state)
+        const int rr = min(r, r_end - 1);
+        const int start = starts[rr];
+        const int prev_start = rr > 0 ? starts[rr - 1] : start;
         const int d = start - prev_start;
-        const double mu = (row_ok && pc.rm) ? __ldg(pc.rm + r) : 0.0;
-        const double sd = (row_ok && pc.rs_) ? __ldg(pc.rs_ + r) : 1.0;
+        const double mu = pc.rm ? __ldg(pc.rm + rr) : 0.0;
+        const double sd = pc.rs_ ? __ldg(pc.rs_ + rr) : 1.0;
         const double inv_sd = __drcp_rn(sd);
         int lo = 0, hi = W;
         double maskval = pc.mask_fill;
@@ -622,20 +625,70 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
         // uniform time bounds of the strip
         const int start_first = __shfl_sync(TB2_FULL_MASK, start, 0);
         const int start_last = __shfl_sync(TB2_FULL_MASK, start, lane_last);
-        int dmax = row_ok ? d : 0;
+        int dmax = row_ok ? d : 0, dmin = row_ok ? d : 0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) dmax = max(dmax, __shfl_xor_sync(TB2_FULL_MASK, dmax, off));
+        for (int off = 16; off > 0; off >>= 1) {
+            dmax = max(dmax, __shfl_xor_sync(TB2_FULL_MASK, dmax, off));
+            dmin = min(dmin, __shfl_xor_sync(TB2_FULL_MASK, dmin, off));
+        }
+        // predicated ("lean") steps and the steady state need band starts that never
+        // move left; anything else takes the fully general step
+        const bool lean = FAST && dmin >= 0;
         const int t_begin = start_first;
         const int t_end = start_last + W - 1 + lane_last;
         // steady state: every lane of a full strip is inside its band with j >= 1 and
         // both cells of the row above available
         int t_lo = start_last + lane_last + 1, t_hi = start_first + W - 2 - dmax;
-        if (!FAST || lane_last != 31) { t_lo = t_end + 1; t_hi = t_end; }   // general path only
+        if (!lean) { t_lo = t_end + 1; t_hi = t_end; }   // general path only
         double x = 0.0, xout = 0.0, up_prev = 0.0;
         uint32_t cw = 0u;
-        int j = t_begin - lane - start;
-        const double *ep = em + (t_begin - lane);
+        const int lane_eff = min(lane, lane_last);
+        int j = t_begin - lane_eff - start;
+        const double *ep = em + (t_begin - lane_eff);
         int t = t_begin;
+        // ---------- lean step: every band-edge rule of the general step folded into
+        // three range tests (row active, cell above valid, cell above-left valid); the
+        // first cell of a row falls out of x = -inf (stay impossible) and of the ranges:
+        // d == 0 -> above-left invalid -> forced skip, d >= 1 -> above invalid at j = 0 ->
+        // forced diagonal, exactly as _c_dynamic_programming.pyx:213-234 ----------
+        const int w_act = row_ok ? W : 0;
+        const int julo = d >= 1 ? 1 : 0, jllo = 1 - julo;
+        const unsigned n_u = (unsigned)max(W - d - julo, 0), n_ul = (unsigned)max(W - d - jllo + 1, 0);
+#define TB2_WF_LEAN_STEP()                                                                      \
+        {                                                                                       \
+            double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);                                 \
+            if (lane == 0 && (unsigned)(j + d) < (unsigned)W) up = tb2_rb_ld<RBS>(rowbuf, rb_s, j + d); \
+            const double upl = up_prev;                                                         \
+            up_prev = up;                                                                       \
+            const bool act = (unsigned)j < (unsigned)w_act;                                     \
+            const double u = ((unsigned)(j - julo) < n_u) ? up : NEG;                           \
+            const double ul = ((unsigned)(j - jllo) < n_ul) ? upl : NEG;                        \
+            const double z = act ? tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval,  \
+                                                       zrow, zs, mhz) : 0.0;                    \
+            const double a = (x - stay) + z;                                                    \
+            double cc = ul + z;                                                                 \
+            uint32_t code = 2u;                                                                 \
+            const double sk = u - skip;                                                         \
+            if (sk > cc) { cc = sk; code = 1u; }                                                \
+            double nx = a;                                                                      \
+            if (cc > a) nx = cc; else code = 0u;                                                \
+            const int tq = (t - t_begin) & 15;                                                  \
+            if (act) {                                                                          \
+                x = nx; xout = nx;                                                              \
+                cw |= code << (2 * tq);                                                         \
+                if (is_tail) tb2_rb_st<RBS>(rowbuf, rb_s, j, nx);                               \
+            }                                                                                   \
+            if (tq == 15 || t == t_end) {                                                       \
+                tbs[((t - t_begin) >> 4) * 32 + lane] = cw;                                     \
+                cw = 0u;                                                                        \
+            }                                                                                   \
+            ++j; ++ep;                                                                          \
+        }
+        if (lean) {
+            x = NEG;
+            if (lane == 0 && d >= 1) up_prev = tb2_rb_ld<RBS>(rowbuf, rb_s, d - 1);
+            for (; t <= t_end && (t < t_lo || ((t - t_begin) & 15) != 0); ++t) TB2_WF_LEAN_STEP()
+        }
         // ---------- general step (prologue / epilogue / partial strips) ----------
 #define TB2_WF_GENERAL_STEP()                                                                   \
         {                                                                                       \
@@ -685,8 +738,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
             }                                                                                   \
             ++j; ++ep;                                                                          \
         }
-        for (; t <= t_end && (t < t_lo || ((t - t_begin) & 15) != 0); ++t) TB2_WF_GENERAL_STEP()
-        if (FAST && t + 15 <= t_hi) {
+        if (lean && t + 15 <= t_hi) {
             // ---------- steady state: groups of 16 steps, no band-edge predicates, z one
             // step ahead, one coalesced move-word store per group ----------
             double z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval, nullptr, zs, mhz);
@@ -706,8 +758,13 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
             }
             cw = 0u;
         }
-        for (; t <= t_end; ++t) TB2_WF_GENERAL_STEP()
+        if (lean) {
+            for (; t <= t_end; ++t) TB2_WF_LEAN_STEP()
+        } else {
+            for (; t <= t_end; ++t) TB2_WF_GENERAL_STEP()
+        }
 #undef TB2_WF_GENERAL_STEP
+#undef TB2_WF_LEAN_STEP
         tbs += (((t_end - t_begin) >> 4) + 1) * 32;
         __syncwarp();
     }
