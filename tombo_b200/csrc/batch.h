@@ -33,13 +33,14 @@ struct ReadState {
 struct BatchView {
     int n_reads;
     int kmer_width;
+    int max_raw;       // longest raw signal of the batch (samples)
     const long long *raw_off, *seq_off, *base_off, *ev_off;
     const unsigned char *seq;
     double *rawf;      // raw signal as fp64 (reversed for RNA)          [sum S]
     double *norm;      // normalised signal of the current call         [sum S]
     double *cs;        // cumulative sums / candidate scores scratch    [sum S + n]
     double *scores;    //                                               [sum S]
-    unsigned char *cstate;  //                                          [sum S]
+    unsigned char *cstate;  // changepoint bit sets (spill)                [2 sum S + 2 n + 8]
     int *cpts;         // changepoints                                  [sum E]
     double *em;        // event means                                   [sum E]
     double *rm, *rs;   // expected levels                               [sum B]

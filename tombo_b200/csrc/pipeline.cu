@@ -62,6 +62,9 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
         hb.base_off[r + 1] = hb.base_off[r] + nb;
         hb.ev_off[r + 1] = hb.ev_off[r] + std::max<long long>(2, num_events_of(s, nb, p, ratio)) + 1;
     }
+    long long max_raw = 0;
+    for (int r = 0; r < n; ++r) max_raw = std::max<long long>(max_raw, raw_off[r + 1] - raw_off[r]);
+    v.max_raw = (int)max_raw;
     hb.total_s = raw_off[n] - raw_off[0];
     hb.total_seq = seq_off[n] - seq_off[0];
     hb.total_b = hb.base_off[n];
@@ -79,7 +82,7 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
     TB2_CUDA_TRY(ctx, P[B_NORM].reserve(S * 8 + 8));
     TB2_CUDA_TRY(ctx, P[B_CS].reserve((S + n) * 8 + 8));
     TB2_CUDA_TRY(ctx, P[B_SCORES].reserve(S * 8 + 8));
-    TB2_CUDA_TRY(ctx, P[B_CSTATE].reserve(S + 8));
+    TB2_CUDA_TRY(ctx, P[B_CSTATE].reserve(2 * S + 128 * (size_t)n + 16));
     TB2_CUDA_TRY(ctx, P[B_CPTS].reserve(E * 4 + 8));
     TB2_CUDA_TRY(ctx, P[B_EM].reserve(E * 8 + 8));
     TB2_CUDA_TRY(ctx, P[B_RM].reserve(Bn * 8 + 8));

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #define TB2_SEL_THREADS 256
+#define TB2_SEL_SMALL 64      // candidates left at which the select finishes by ranking
 
 __device__ __forceinline__ unsigned long long tb2_key(double v)
 {
@@ -26,6 +27,9 @@ struct SelectSmem {
     unsigned int sel_bin, sel_below, sel_cnt;
     unsigned long long red_u64[8];
     unsigned int red_u32[8];
+    unsigned long long small[TB2_SEL_SMALL];   // finishing list of the radix select
+    unsigned long long result;
+    unsigned int n_small;
 };
 
 // block-wide sum of an unsigned (all threads get the result)
@@ -104,7 +108,31 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
         prefix |= (unsigned long long)sm.sel_bin << shift;
         mask |= 0xffULL << shift;
         kk -= sm.sel_below;
+        const unsigned int left = sm.sel_cnt;
+        if (tid == 0) sm.n_small = 0;
         __syncthreads();
+        if (left <= TB2_SEL_SMALL && shift > 0) {
+            // few candidates share the digits fixed so far: list them and rank directly
+            for (int i = tid; i < n; i += TB2_SEL_THREADS) {
+                if (!pred(i)) continue;
+                const unsigned long long key = tb2_key(f(i));
+                if ((key & mask) == prefix) sm.small[atomicAdd(&sm.n_small, 1u)] = key;
+            }
+            __syncthreads();
+            if (tid < (int)left) {
+                const unsigned long long mine = sm.small[tid];
+                unsigned int rank = 0;
+                for (unsigned int q = 0; q < left; ++q) {
+                    const unsigned long long o = sm.small[q];
+                    rank += (o < mine) || (o == mine && q < (unsigned int)tid);
+                }
+                if (rank == kk) sm.result = mine;
+            }
+            __syncthreads();
+            const unsigned long long res = sm.result;
+            __syncthreads();
+            return res;
+        }
     }
     return prefix;
 }

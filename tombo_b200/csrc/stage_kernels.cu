@@ -190,21 +190,35 @@ __device__ __forceinline__ bool cand_gt(double si, int i, double sk, int k)
     return si > sk || (si == sk && i > k);
 }
 
-__global__ void __launch_bounds__(ST_THREADS)
-k_cpts(BatchView b, tb2_params p, int on_raw)
+// bit i of word w <-> candidate 32 w + i.  X(i + o) / X(i - o) as words aligned to i.
+__device__ __forceinline__ uint32_t cp_shr(const uint32_t *x, int w, int nw, int o)
 {
+    const uint32_t hi = (w + 1 < nw) ? x[w + 1] : 0u;
+    return (x[w] >> o) | (hi << (32 - o));
+}
+__device__ __forceinline__ uint32_t cp_shl(const uint32_t *x, int w, int o)
+{
+    const uint32_t lo = (w > 0) ? x[w - 1] : 0u;
+    return (x[w] << o) | (lo >> (32 - o));
+}
+
+#define CP_MAX_OFF 12   // exclusion zones up to +-12 candidates run bit-parallel
+
+__global__ void __launch_bounds__(ST_THREADS)
+k_cpts(BatchView b, tb2_params p, int on_raw, int smem_words)
+{
+    extern __shared__ uint32_t cp_smem[];
     __shared__ SelectSmem sm;
-    __shared__ int s_flag;
+    __shared__ int s_flag, s_pos;
     const int r = blockIdx.x;
     ReadState &s = b.st[r];
     if (!rd_active(s)) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long ro = b.raw_off[r];
     const int n = (int)(b.raw_off[r + 1] - ro);
     const double *sig = (on_raw ? b.rawf : b.norm) + ro;
     double *cs = b.cs + ro + r;
     double *sc = b.scores + ro;
-    volatile unsigned char *state = b.cstate + ro;
     const int w = (int)p.running_stat_width, m = (int)p.min_obs_per_base;
     const int N = s.num_events;
     int n_cand, bound;
@@ -229,10 +243,8 @@ k_cpts(BatchView b, tb2_params p, int on_raw)
             }
         }
         __syncthreads();
-        for (int i = tid; i < n_cand; i += ST_THREADS) {
+        for (int i = tid; i < n_cand; i += ST_THREADS)
             sc[i] = fabs(((2 * cs[i + w]) - cs[i]) - cs[i + 2 * w]);   // :95-98
-            state[i] = 0;
-        }
     } else {
         n_cand = n - 2 * w;
         bound = n_cand;      // :199
@@ -250,102 +262,157 @@ k_cpts(BatchView b, tb2_params p, int on_raw)
             else if (m1 > m2) t = (m1 - m2) / sqrt(var1 + var2);
             else t = (m2 - m1) / sqrt(var1 + var2);
             sc[pos] = t;
-            state[pos] = 0;
         }
     }
     if (N < 1 || N > n_cand) { if (tid == 0) s.status = (N < 1) ? TB2_ERR_UNEXPECTED : TB2_ERR_FEWER_CPTS; return; }
     __syncthreads();
-    // ---- greedy exclusion as a fixed point ----
-    for (;;) {
-        if (tid == 0) s_flag = 0;
-        __syncthreads();
-        int undecided = 0;
-        for (int i = tid; i < n_cand; i += ST_THREADS) {
-            if (state[i] != 0) continue;
-            const double si = sc[i];
-            bool acc_nb = false, blocked = false;
-            const int k0 = max(0, i - m + 1), k1 = min(n_cand - 1, i + m - 1);
-            for (int k = k0; k <= k1; ++k) {
-                if (k == i) continue;
-                const unsigned char stt = state[k];
-                if (stt == 1) acc_nb = true;
-                else if (stt == 0 && cand_gt(sc[k], k, si, i)) blocked = true;
-            }
-            if (acc_nb) state[i] = 2;
-            else if (!blocked) state[i] = 1;
-            else undecided = 1;
+    // ---- greedy exclusion as a fixed point, 32 candidates per word ----
+    // A = accepted, D = decided, G_o bit i = "candidate i + o outranks candidate i".
+    // A round accepts every undecided candidate whose zone holds no accepted and no
+    // undecided higher-ranked candidate, and rejects those with an accepted one in
+    // their zone (Jacobi sweep on double buffers: decisions are final and are exactly
+    // the ranked greedy's, whatever the sweep order).
+    const int nw = (n_cand + 31) >> 5;
+    const int no = m - 1;                       // zone half-width
+    uint32_t *bits;
+    if ((4 + max(no, 0)) * nw <= smem_words) bits = cp_smem;
+    else bits = reinterpret_cast<uint32_t *>(b.cstate + ((2 * ro + 128LL * r + 3) & ~3LL));
+    if (no > CP_MAX_OFF) { if (tid == 0) s.status = TB2_ERR_CAPACITY; return; }
+    uint32_t *A0 = bits, *A1 = bits + nw, *D0 = bits + 2 * nw, *D1 = bits + 3 * nw, *G = bits + 4 * nw;
+    for (int wd = warp; wd < nw; wd += ST_THREADS / 32) {
+        const int i = wd * 32 + lane;
+        const bool valid = i < n_cand;
+        const double si = valid ? sc[i] : 0.0;
+        for (int o = 1; o <= no; ++o) {
+            const bool gt = valid && (i + o < n_cand) && cand_gt(sc[i + o], i + o, si, i);
+            const uint32_t g = __ballot_sync(TB2_FULL_MASK, gt);
+            if (lane == 0) G[(o - 1) * nw + wd] = g;
         }
-        if (undecided) s_flag = 1;
-        __syncthreads();
-        const int again = s_flag;
-        __syncthreads();
+        const uint32_t inv = __ballot_sync(TB2_FULL_MASK, !valid);
+        if (lane == 0) { A0[wd] = 0u; D0[wd] = inv; }
+    }
+    __syncthreads();
+    uint32_t *Ac = A0, *An = A1, *Dc = D0, *Dn = D1;
+    for (;;) {
+        int undecided = 0;
+        for (int wd = tid; wd < nw; wd += ST_THREADS) {
+            const uint32_t a = Ac[wd], dd = Dc[wd];
+            const uint32_t U = ~dd;
+            uint32_t na = a, nd = dd;
+            if (U != 0u) {
+                uint32_t accnb = 0u, blocked = 0u;
+                for (int o = 1; o <= no; ++o) {
+                    const uint32_t *Go = G + (o - 1) * nw;
+                    accnb |= cp_shr(Ac, wd, nw, o) | cp_shl(Ac, wd, o);
+                    // undecided neighbours: bits of ~D, out-of-range words read as decided
+                    const uint32_t d_hi = (wd + 1 < nw) ? Dc[wd + 1] : ~0u;
+                    const uint32_t d_lo = (wd > 0) ? Dc[wd - 1] : ~0u;
+                    const uint32_t u_up = ~((dd >> o) | (d_hi << (32 - o)));
+                    const uint32_t u_dn = ~((dd << o) | (d_lo >> (32 - o)));
+                    const uint32_t g_up = Go[wd];
+                    const uint32_t g_dn = ~cp_shl(Go, wd, o);     // i - o outranks i
+                    blocked |= (u_up & g_up) | (u_dn & g_dn);
+                }
+                const uint32_t rej = U & accnb;
+                const uint32_t acc = U & ~accnb & ~blocked;
+                na = a | acc;
+                nd = dd | rej | acc;
+                if (~nd != 0u) undecided = 1;
+            }
+            An[wd] = na; Dn[wd] = nd;
+        }
+        const int again = __syncthreads_or(undecided);
+        uint32_t *tA = Ac; Ac = An; An = tA;
+        uint32_t *tD = Dc; Dc = Dn; Dn = tD;
         if (!again) break;
     }
+    const uint32_t *A = Ac;      // final accepted set
+    uint32_t *K = An;            // scratch: kept set
     // ---- keep the N best accepted ----
     unsigned int acc_cnt = 0;
-    for (int i = tid; i < n_cand; i += ST_THREADS) acc_cnt += (state[i] == 1);
+    for (int wd = tid; wd < nw; wd += ST_THREADS) acc_cnt += __popc(A[wd]);
     acc_cnt = tb2_block_sum(acc_cnt, sm);
     if ((int)acc_cnt < N) { if (tid == 0) s.status = TB2_ERR_FEWER_CPTS; return; }
     double vN, dummy;
     auto f_score = [&](int i) { return sc[i]; };
-    auto p_acc = [&](int i) { return state[i] == 1; };
+    auto p_acc = [&](int i) { return (A[i >> 5] >> (i & 31)) & 1u; };
     tb2_block_select2(f_score, p_acc, n_cand, (int)acc_cnt - N, false, &vN, &dummy, sm);
-    unsigned int g = 0, e = 0;
+    if (tid == 0) s_pos = -1;
+    __syncthreads();
+    unsigned int g = 0, e = 0, higher = 0, eq_all = 0;
     for (int i = tid; i < n_cand; i += ST_THREADS) {
-        if (state[i] != 1) continue;
-        g += sc[i] > vN;
-        e += sc[i] == vN;
+        const double v = sc[i];
+        const bool acc = p_acc(i);
+        higher += v > vN;
+        if (v == vN) {
+            ++eq_all;
+            if (acc) { ++e; s_pos = i; }
+        }
+        g += acc && v > vN;
     }
     g = tb2_block_sum(g, sm);
     e = tb2_block_sum(e, sm);
+    eq_all = tb2_block_sum(eq_all, sm);
+    higher = tb2_block_sum(higher, sm);
     const int need = N - (int)g;   // 1 <= need <= e, taken from the largest positions
     int posN;
-    {
+    if (e == 1u) {
+        posN = s_pos;              // the usual case: the N-th score is unique
+    } else {
         auto f_pos = [&](int i) { return (double)i; };
-        auto p_tie = [&](int i) { return state[i] == 1 && sc[i] == vN; };
+        auto p_tie = [&](int i) { return p_acc(i) && sc[i] == vN; };
         double pv, pd;
         tb2_block_select2(f_pos, p_tie, n_cand, (int)e - need, false, &pv, &pd, sm);
         posN = (int)pv;
     }
     // rank index of the N-th pick in the full candidate order (:109-118)
-    unsigned int higher = 0;
-    for (int i = tid; i < n_cand; i += ST_THREADS)
-        higher += (sc[i] > vN) || (sc[i] == vN && i > posN);
-    higher = tb2_block_sum(higher, sm);
+    if (eq_all > 1u) {
+        unsigned int h2 = 0;
+        for (int i = tid; i < n_cand; i += ST_THREADS) h2 += (sc[i] == vN && i > posN);
+        higher += tb2_block_sum(h2, sm);
+    }
     if (N > 1 && (int)higher + 1 >= bound) { if (tid == 0) s.status = TB2_ERR_FEWER_CPTS; return; }
     // ---- ordered compaction (+ w), dropping changepoints inside stalls ----
-    const int per = (n_cand + ST_THREADS - 1) / ST_THREADS;
-    const int i0 = min(n_cand, tid * per), i1 = min(n_cand, i0 + per);
     const int *si = b.stall_ints ? b.stall_ints + 2 * (size_t)b.stall_cap * r : nullptr;
     const int ns = b.stall_ints ? s.n_stalls : 0;
-    auto keep = [&](int i) {
-        if (state[i] != 1) return false;
-        if (!(sc[i] > vN || (sc[i] == vN && i >= posN))) return false;
-        const int c = i + w;
-        for (int k = 0; k < ns; ++k) if (si[2 * k] < c && c < si[2 * k + 1]) return false;
-        return true;
-    };
+    for (int wd = warp; wd < nw; wd += ST_THREADS / 32) {
+        const int i = wd * 32 + lane;
+        bool keep = (A[wd] >> lane) & 1u;
+        if (keep) {
+            const double v = sc[i];
+            keep = v > vN || (v == vN && i >= posN);
+            const int c = i + w;
+            for (int k = 0; keep && k < ns; ++k) if (si[2 * k] < c && c < si[2 * k + 1]) keep = false;
+        }
+        const uint32_t kw = __ballot_sync(TB2_FULL_MASK, keep);
+        if (lane == 0) K[wd] = kw;
+    }
+    __syncthreads();
+    const int per = (nw + ST_THREADS - 1) / ST_THREADS;
+    const int w0 = min(nw, tid * per), w1 = min(nw, w0 + per);
     unsigned int mine = 0;
-    for (int i = i0; i < i1; ++i) mine += keep(i);
-    // exclusive scan over threads
-    const int lane = tid & 31, warp = tid >> 5;
+    for (int wd = w0; wd < w1; ++wd) mine += __popc(K[wd]);
     unsigned int inc = mine;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const unsigned int o = __shfl_up_sync(TB2_FULL_MASK, inc, off);
         if (lane >= off) inc += o;
     }
-    __syncthreads();
     if (lane == 31) sm.warp_tot[warp] = inc;
     __syncthreads();
     unsigned int base = 0, total = 0;
     for (int q = 0; q < ST_THREADS / 32; ++q) { if (q < warp) base += sm.warp_tot[q]; total += sm.warp_tot[q]; }
     unsigned int o = base + inc - mine;
     int *cp = b.cpts + b.ev_off[r];
-    for (int i = i0; i < i1; ++i) if (keep(i)) cp[o++] = i + w;
-    if (tid == 0) {
-        s.n_cpts = (int)total;
+    for (int wd = w0; wd < w1; ++wd) {
+        uint32_t kw = K[wd];
+        while (kw) {
+            const int bit = __ffs(kw) - 1;
+            kw &= kw - 1u;
+            cp[o++] = wd * 32 + bit + w;
+        }
     }
+    if (tid == 0) s.n_cpts = (int)total;
 }
 
 // ===========================================================================
@@ -1095,7 +1162,12 @@ int tb2_launch_normalize(tb2_ctx *ctx, const BatchView &b, const StagePolicy &po
 
 int tb2_launch_cpts(tb2_ctx *ctx, const BatchView &b, const tb2_params &p, int on_raw)
 {
-    k_cpts<<<b.n_reads, ST_THREADS, 0, ctx->stream>>>(b, p, on_raw);
+    // bit sets of the greedy pass: 4 + (min_obs_per_base - 1) words per 32 candidates, in
+    // shared memory when the longest read of the batch fits (else the read's scratch)
+    const long long nw = (b.max_raw + 32) / 32;
+    long long words = (4 + std::max(0, (int)p.min_obs_per_base - 1)) * nw;
+    if (words * 4 > 64 * 1024) words = 0;
+    k_cpts<<<b.n_reads, ST_THREADS, (size_t)words * 4, ctx->stream>>>(b, p, on_raw, (int)words);
     TB2_CHECK_LAUNCH(ctx);
     return TB2_OK;
 }
