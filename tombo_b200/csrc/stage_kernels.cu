@@ -204,12 +204,13 @@ __device__ __forceinline__ uint32_t cp_shl(const uint32_t *x, int w, int o)
 
 #define CP_MAX_OFF 12   // exclusion zones up to +-12 candidates run bit-parallel
 
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, 5)
 k_cpts(BatchView b, tb2_params p, int on_raw, int smem_words)
 {
     extern __shared__ uint32_t cp_smem[];
     __shared__ SelectSmem sm;
-    __shared__ int s_flag, s_pos;
+    __shared__ double s_x[256];
+    __shared__ int s_pos;
     const int r = blockIdx.x;
     ReadState &s = b.st[r];
     if (!rd_active(s)) return;
@@ -227,19 +228,37 @@ k_cpts(BatchView b, tb2_params p, int on_raw, int smem_words)
         bound = n_cand - 2 * w;  // num_cands = candidate_poss.shape[0] - 2*w (:105-106)
         if (n_cand <= 0) { if (tid == 0) s.status = TB2_ERR_UNEXPECTED; return; }
         // np.cumsum(concatenate([[0.0], signal])): strictly sequential fp64 sums.
-        // One warp; every lane carries the running sum through 32 shuffled adds.
+        // One warp stages 256 samples in shared memory (coalesced), then every lane
+        // carries the same running sum through them (broadcast reads issued ahead of
+        // the adds, so the serial chain is the add latency alone); lane k keeps the
+        // prefix sums of elements k, k + 32, ... for a coalesced store.
         if (tid < 32) {
             double acc = 0.0;
             if (tid == 0) cs[0] = 0.0;
-            for (int base = 0; base < n; base += 32) {
-                const double x = (base + tid < n) ? sig[base + tid] : 0.0;
-                double mine = 0.0;
+            for (int base = 0; base < n; base += 256) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    acc = acc + __shfl_sync(TB2_FULL_MASK, x, k);
-                    if (tid == k) mine = acc;
+                for (int q = 0; q < 8; ++q) {
+                    const int i = base + q * 32 + tid;
+                    s_x[q * 32 + tid] = (i < n) ? sig[i] : 0.0;
                 }
-                if (base + tid < n) cs[base + tid + 1] = mine;
+                __syncwarp();
+                double mine[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    double m_q = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        acc = acc + s_x[q * 32 + k];
+                        if (tid == k) m_q = acc;
+                    }
+                    mine[q] = m_q;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = base + q * 32 + tid;
+                    if (i < n) cs[i + 1] = mine[q];
+                }
             }
         }
         __syncthreads();
@@ -789,11 +808,15 @@ __device__ unsigned long long g_tb2_counters[8];
 
 #define TS_ABINS 4096   // bins of the approximate (fp32) pre-pass
 
+#define TS_PAD 1024     // TS_MAX rounded up to a power of two (bitonic sort by ev)
+
 struct TsSmem {
-    double ev[TS_MAX], md[TS_MAX];
-    float evf[TS_MAX], mdf[TS_MAX];
-    unsigned int hist[TS_ABINS + 2];   // also holds the TS_BINS + 2 exact bins
-    double buf[TS_BUF];
+    double ev[TS_PAD], md[TS_PAD];     // points, sorted by ev once the bracket sample is taken
+    float4 pt[TS_PAD];                 // fp32 images: pass 1 (ev, md), pass 2 (qL, qH, ev)
+    union {
+        unsigned int hist[TS_ABINS + 2];   // also holds the TS_BINS + 2 exact bins
+        double buf[TS_BUF];                // bracket sample, then the slopes inside the bracket
+    };
     unsigned int nbuf, b1, b2, below, maxabs_bits;
     int ok;
 };
@@ -868,18 +891,45 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
     const long long k1 = even ? Np / 2 - 1 : Np / 2;   // ranks k1 (and k1+1 if even)
     double v1 = 0, v2 = 0;
     bool have = false;
-    // ---- bracket from a sample of n/2 independent pairs ----
+    // ---- bracket [lo, hi] from a sample of n/2 independent pairs (original order) ----
     const int hs = n / 2;
-    // ---- fast path: fp32 pre-pass picks a bracket [L, H), then ONE exact pass counts
-    // the slopes below L and collects those inside; every decision of that pass is
-    // exact (products with an error guard, the true fp64 division whenever a pair is
-    // within the guard or inside the bracket), so the selected order statistics are
-    // the same doubles np.median sees.  If the bracket misses, fall through.
-    if (hs >= 16 && Np > 4 * TS_ABINS) {
-        auto f_samp = [&](int i) { return ts_slope(t, i, i + hs); };
-        double lo, hi, d0;
+    double lo = 0, hi = 0;
+    if (hs >= 16) {
+        for (int i = tid; i < hs; i += ST_THREADS) t.buf[i] = ts_slope(t, i, i + hs);
+        __syncthreads();
+        double d0;
+        auto f_samp = [&](int i) { return t.buf[i]; };
         tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.30), false, &lo, &d0, sm);
         tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.70), false, &hi, &d0, sm);
+    }
+    // ---- sort the points by ev: slope(i, j) is symmetric in (i, j) (both differences
+    // negate exactly), so the multiset of slopes is unchanged, and every pair a < b now
+    // has ev_a - ev_b <= 0, which fixes the direction of the screening inequalities ----
+    {
+        int P = 2;
+        while (P < n) P <<= 1;
+        for (int i = n + tid; i < P; i += ST_THREADS) { t.ev[i] = __longlong_as_double(0x7ff0000000000000LL); t.md[i] = 0.0; }
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int idx = tid; idx < (P >> 1); idx += ST_THREADS) {
+                    const int a = ((idx & ~(jj - 1)) << 1) | (idx & (jj - 1)), c = a | jj;
+                    const double ea = t.ev[a], ec = t.ev[c];
+                    if ((ea > ec) == ((a & k) == 0)) {
+                        t.ev[a] = ec; t.ev[c] = ea;
+                        const double ma = t.md[a]; t.md[a] = t.md[c]; t.md[c] = ma;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // ---- fast path: fp32 pre-pass picks a bracket [L, H), then ONE exact pass counts
+    // the slopes below L and collects those inside; every decision of that pass is
+    // exact (a guarded fp32 screen, the true fp64 division whenever a pair is within
+    // the guard or inside the bracket), so the selected order statistics are the same
+    // doubles np.median sees.  If the bracket misses, fall through.
+    if (hs >= 16 && Np > 4 * TS_ABINS) {
         const float lo_f = (float)lo, hi_f = (float)hi;
         const float w_f = (hi_f - lo_f) / (float)TS_ABINS;
         if (hi_f > lo_f && w_f > 0.0f && isfinite(w_f)) {
@@ -889,8 +939,9 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             {
                 float mx = 0.0f;
                 for (int i = tid; i < n; i += ST_THREADS) {
-                    t.evf[i] = (float)t.ev[i]; t.mdf[i] = (float)t.md[i];
-                    mx = fmaxf(mx, fmaxf(fabsf(t.evf[i]), fabsf(t.mdf[i])));
+                    const float ef = (float)t.ev[i], mf = (float)t.md[i];
+                    t.pt[i] = make_float4(ef, mf, 0.0f, 0.0f);
+                    mx = fmaxf(mx, fmaxf(fabsf(ef), fabsf(mf)));
                 }
                 if (!(mx < 3.0e38f)) mx = 3.0e38f;          // inf / nan: everything is screened out
                 atomicMax(&t.maxabs_bits, __float_as_uint(mx));
@@ -900,8 +951,9 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             __syncthreads();
             unsigned int n_under = 0, n_over = 0;   // 60 % of the pairs: counted in registers
             ts_for_pairs(n, [&](int i, int j) {
-                const float de = t.evf[i] - t.evf[j];
-                const float sa = (de == 0.0f) ? 1000.0f : __fdividef(t.mdf[i] - t.mdf[j], de);
+                const float4 pi = t.pt[i], pj = t.pt[j];
+                const float de = pi.x - pj.x;
+                const float sa = (de == 0.0f) ? 1000.0f : __fdividef(pi.y - pj.y, de);
                 if (sa < lo_f) ++n_under;
                 else if (!(sa < hi_f)) ++n_over;
                 else atomicAdd(&t.hist[min(TS_ABINS - 1, (int)((sa - lo_f) * inv_w)) + 1], 1u);
@@ -942,38 +994,40 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                 // exact bracket with a one-bin margin on both sides
                 const double L = (double)lo_f + (double)w_f * (double)(bA - 2);
                 const double H = (double)lo_f + (double)w_f * (double)(bB + 1);
-                // fp32 screen: with |values| <= M the float images carry an absolute
-                // error <= 1.3e-7 * M each, so E = dm - T*de is known to within
-                // g(T) = 1e-5 * M * (1 + |T|); outside that guard the side of T is
-                // certain, inside it the pair takes the exact fp64 path.
+                // fp32 screen.  With Q_T(k) = md_k - T * ev_k, a pair a < b (ev_a <= ev_b)
+                // has slope < T  <=>  Q_T(a) > Q_T(b)  and  slope >= T  <=>  Q_T(a) <= Q_T(b)
+                // whenever ev_a != ev_b.  The fp32 images q = fma(-T_f, ev_f, md_f) carry an
+                // absolute error <= 1.8e-7 * M * (1 + |T|) each (|values| <= M), so a
+                // difference beyond g(T) = 1e-5 * M * (1 + |T|) settles the side of T with a
+                // margin far above the 3 ulp between the exact quotient and the reference's
+                // rounded one; anything closer, and every pair whose fp32 ev images
+                // coincide (ev_a == ev_b gives the reference's 1000.0), takes the exact
+                // fp64 path.
                 const float M = fmaxf(1.0f, __uint_as_float(t.maxabs_bits));
                 const float Lf = (float)L, Hf = (float)H;
                 const float gLf = 1e-5f * M * (1.0f + fabsf(Lf)), gHf = 1e-5f * M * (1.0f + fabsf(Hf));
                 __syncthreads();
+                for (int i = tid; i < n; i += ST_THREADS) {
+                    const float ef = t.pt[i].x, mf = t.pt[i].y;
+                    t.pt[i] = make_float4(fmaf(-Lf, ef, mf), fmaf(-Hf, ef, mf), ef, 0.0f);
+                }
+                __syncthreads();     // hist is dead from here on: buf takes its place
                 unsigned int below = 0;
                 ts_for_pairs(n, [&](int i, int j) {
-                    int cls = 2;      // -1: s < L, 0: L <= s < H, +1: s >= H, 2: undecided
-                    double sv = 1000.0;
-                    {
-                        const float def = t.evf[i] - t.evf[j], dmf = t.mdf[i] - t.mdf[j];
-                        if (fabsf(def) > 1e-3f * M) {
-                            const float eL = dmf - Lf * def, eH = dmf - Hf * def;
-                            const bool pos = def > 0.0f;
-                            // s < L  <=>  (dm - L*de) has the sign opposite to de
-                            if (pos ? (eL < -gLf) : (eL > gLf)) cls = -1;
-                            else if (pos ? (eH > gHf) : (eH < -gHf)) cls = 1;
-                        }
-                    }
-                    if (cls == 2) {
+                    const float4 pi = t.pt[i], pj = t.pt[j];
+                    const bool lowc = (pi.x - pj.x) > gLf;        // certainly slope < L
+                    const bool highc = (pi.y - pj.y) < -gHf;      // certainly slope >= H
+                    if ((lowc || highc) && pi.z != pj.z) {
+                        below += lowc;
+                    } else {
                         const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
                         // the reference's value (_c_helper.pyx:371-376)
-                        sv = (de == 0.0) ? 1000.0 : dm / de;
-                        cls = (sv < L) ? -1 : ((sv < H) ? 0 : 1);
-                    }
-                    if (cls < 0) ++below;
-                    else if (cls == 0) {
-                        const unsigned int slot = atomicAdd(&t.nbuf, 1u);
-                        if (slot < TS_BUF) t.buf[slot] = sv;
+                        const double sv = (de == 0.0) ? 1000.0 : dm / de;
+                        if (sv < L) ++below;
+                        else if (sv < H) {
+                            const unsigned int slot = atomicAdd(&t.nbuf, 1u);
+                            if (slot < TS_BUF) t.buf[slot] = sv;
+                        }
                     }
                 });
                 below = tb2_block_sum(below, sm);
@@ -991,10 +1045,6 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
         }
     }
     if (!have && hs >= 16) {
-        auto f_samp = [&](int i) { return ts_slope(t, i, i + hs); };
-        double lo, hi, d0;
-        tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.30), false, &lo, &d0, sm);
-        tb2_block_select2(f_samp, PredAll(), hs, (int)(hs * 0.70), false, &hi, &d0, sm);
         if (hi > lo) {
             const double inv_w = (double)TS_BINS / (hi - lo);
             auto bin_of = [&](double v) -> int {
