@@ -25,7 +25,7 @@ struct SelectSmem {
     unsigned int hist[256];
     unsigned int warp_tot[8];
     unsigned int sel_bin, sel_below, sel_cnt;
-    unsigned long long red_u64[8];
+    unsigned long long red_u64[8], red_and[8];
     unsigned int red_u32[8];
     unsigned long long small[TB2_SEL_SMALL];   // finishing list of the radix select
     unsigned long long result;
@@ -73,7 +73,37 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
     unsigned long long prefix = 0, mask = 0;
     unsigned int kk = (unsigned int)k;
     const int tid = threadIdx.x;
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    // digits shared by every key need no pass: start below the common leading bytes
+    int shift0 = 56;
+    {
+        unsigned long long all_or = 0, all_and = ~0ULL;
+        for (int i = tid; i < n; i += TB2_SEL_THREADS) {
+            if (!pred(i)) continue;
+            const unsigned long long key = tb2_key(f(i));
+            all_or |= key; all_and &= key;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            all_or |= __shfl_xor_sync(TB2_FULL_MASK, all_or, off);
+            all_and &= __shfl_xor_sync(TB2_FULL_MASK, all_and, off);
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { sm.red_u64[tid >> 5] = all_or; sm.red_and[tid >> 5] = all_and; }
+        __syncthreads();
+        all_or = 0; all_and = ~0ULL;
+#pragma unroll
+        for (int w = 0; w < TB2_SEL_THREADS / 32; ++w) { all_or |= sm.red_u64[w]; all_and &= sm.red_and[w]; }
+        const unsigned long long diff = all_or ^ all_and;      // bits that differ somewhere
+        if (diff == 0ULL) { __syncthreads(); return all_or; }   // all keys equal
+        const int top = 63 - __clzll((long long)diff);          // highest differing bit
+        shift0 = (top >> 3) << 3;
+        if (shift0 < 56) {
+            mask = ~0ULL << (shift0 + 8);
+            prefix = all_or & mask;
+        }
+        __syncthreads();
+    }
+    for (int shift = shift0; shift >= 0; shift -= 8) {
         sm.hist[tid] = 0;
         __syncthreads();
         for (int i = tid; i < n; i += TB2_SEL_THREADS) {

@@ -839,6 +839,18 @@ __device__ __forceinline__ void ts_for_pairs(int n, Fn fn)
     }
 }
 
+// the same pairing, one call per column (the callee keeps column j in registers)
+template <class Fn>
+__device__ __forceinline__ void ts_for_cols(int n, Fn fn)
+{
+    const int half = (n + 1) / 2;
+    for (int c = threadIdx.x; c < half; c += ST_THREADS) {
+        const int j0 = c, j1 = n - 1 - c;
+        fn(j0);
+        if (j1 != j0) fn(j1);
+    }
+}
+
 __device__ __forceinline__ void ts_pair_of(long long s, int n, int *pi, int *pj)
 {
     // inverse of the combinations enumeration index
@@ -852,7 +864,7 @@ __device__ __forceinline__ void ts_pair_of(long long s, int n, int *pi, int *pj)
     *pj = (int)(s - row_start(i)) + i + 1;
 }
 
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, 4)
 k_theil_sen(BatchView b, StagePolicy pol, int first_call)
 {
     extern __shared__ unsigned char ts_raw[];
@@ -938,110 +950,138 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             __syncthreads();
             {
                 float mx = 0.0f;
-                for (int i = tid; i < n; i += ST_THREADS) {
-                    const float ef = (float)t.ev[i], mf = (float)t.md[i];
-                    t.pt[i] = make_float4(ef, mf, 0.0f, 0.0f);
-                    mx = fmaxf(mx, fmaxf(fabsf(ef), fabsf(mf)));
-                }
+                for (int i = tid; i < n; i += ST_THREADS)
+                    mx = fmaxf(mx, fmaxf(fabsf((float)t.ev[i]), fabsf((float)t.md[i])));
                 if (!(mx < 3.0e38f)) mx = 3.0e38f;          // inf / nan: everything is screened out
                 atomicMax(&t.maxabs_bits, __float_as_uint(mx));
             }
-            for (int i = tid; i < TS_ABINS + 2; i += ST_THREADS) t.hist[i] = 0;
-            if (tid == 0) { t.nbuf = 0; t.ok = 0; t.below = 0; t.b1 = 0; t.b2 = 0; }
-            __syncthreads();
-            unsigned int n_under = 0, n_over = 0;   // 60 % of the pairs: counted in registers
-            ts_for_pairs(n, [&](int i, int j) {
-                const float4 pi = t.pt[i], pj = t.pt[j];
-                const float de = pi.x - pj.x;
-                const float sa = (de == 0.0f) ? 1000.0f : __fdividef(pi.y - pj.y, de);
-                if (sa < lo_f) ++n_under;
-                else if (!(sa < hi_f)) ++n_over;
-                else atomicAdd(&t.hist[min(TS_ABINS - 1, (int)((sa - lo_f) * inv_w)) + 1], 1u);
-            });
-            n_under = tb2_block_sum(n_under, sm);
-            n_over = tb2_block_sum(n_over, sm);
-            if (tid == 0) { t.hist[0] = n_under; t.hist[TS_ABINS + 1] = n_over; }
-            __syncthreads();
-            // bins holding the (approximate) ranks k1 and k1+1: 256 threads x 17 bins
-            {
-                const int per = (TS_ABINS + 2 + ST_THREADS - 1) / ST_THREADS;
-                const int q0 = min(TS_ABINS + 2, tid * per), q1 = min(TS_ABINS + 2, q0 + per);
-                unsigned int mine = 0;
-                for (int q = q0; q < q1; ++q) mine += t.hist[q];
-                const int lane = tid & 31, warp = tid >> 5;
-                unsigned int inc = mine;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const unsigned int o = __shfl_up_sync(TB2_FULL_MASK, inc, off);
-                    if (lane >= off) inc += o;
-                }
-                if (lane == 31) sm.warp_tot[warp] = inc;
+            // The pre-pass only has to bracket the median ranks, so it looks at the pairs
+            // with (i + j) % stride == 0 (every point takes part equally) and widens the
+            // bracket by 2.5 sigma of the sampled rank; stride is chosen so that the
+            // bracket still fits the buffer (2.5 * sqrt(Np * stride) <~ 1800).  A bracket
+            // that misses or overflows is retried with every pair.
+            int stride = (int)min(8LL, max(1LL, 518400LL / Np));
+            for (; !have && stride >= 1; stride = (stride > 1) ? 1 : 0) {
+                for (int i = tid; i < n; i += ST_THREADS)
+                    t.pt[i] = make_float4((float)t.ev[i], (float)t.md[i], 0.0f, 0.0f);
+                for (int i = tid; i < TS_ABINS + 2; i += ST_THREADS) t.hist[i] = 0;
+                if (tid == 0) { t.nbuf = 0; t.ok = 0; t.below = 0; t.b1 = 0; t.b2 = 0; }
                 __syncthreads();
-                unsigned int base = 0;
-                for (int q = 0; q < warp; ++q) base += sm.warp_tot[q];
-                long long cum = (long long)base + inc - mine;
-                const long long kA = k1, kB = even ? k1 + 1 : k1;
-                for (int q = q0; q < q1; ++q) {
-                    const long long c = t.hist[q];
-                    if (kA >= cum && kA < cum + c) t.b1 = q;
-                    if (kB >= cum && kB < cum + c) t.b2 = q;
-                    cum += c;
-                }
-                __syncthreads();
-            }
-            const int bA = (int)t.b1, bB = (int)t.b2;
-            if (bA >= 1 && bB <= TS_ABINS) {
-                // exact bracket with a one-bin margin on both sides
-                const double L = (double)lo_f + (double)w_f * (double)(bA - 2);
-                const double H = (double)lo_f + (double)w_f * (double)(bB + 1);
-                // fp32 screen.  With Q_T(k) = md_k - T * ev_k, a pair a < b (ev_a <= ev_b)
-                // has slope < T  <=>  Q_T(a) > Q_T(b)  and  slope >= T  <=>  Q_T(a) <= Q_T(b)
-                // whenever ev_a != ev_b.  The fp32 images q = fma(-T_f, ev_f, md_f) carry an
-                // absolute error <= 1.8e-7 * M * (1 + |T|) each (|values| <= M), so a
-                // difference beyond g(T) = 1e-5 * M * (1 + |T|) settles the side of T with a
-                // margin far above the 3 ulp between the exact quotient and the reference's
-                // rounded one; anything closer, and every pair whose fp32 ev images
-                // coincide (ev_a == ev_b gives the reference's 1000.0), takes the exact
-                // fp64 path.
-                const float M = fmaxf(1.0f, __uint_as_float(t.maxabs_bits));
-                const float Lf = (float)L, Hf = (float)H;
-                const float gLf = 1e-5f * M * (1.0f + fabsf(Lf)), gHf = 1e-5f * M * (1.0f + fabsf(Hf));
-                __syncthreads();
-                for (int i = tid; i < n; i += ST_THREADS) {
-                    const float ef = t.pt[i].x, mf = t.pt[i].y;
-                    t.pt[i] = make_float4(fmaf(-Lf, ef, mf), fmaf(-Hf, ef, mf), ef, 0.0f);
-                }
-                __syncthreads();     // hist is dead from here on: buf takes its place
-                unsigned int below = 0;
-                ts_for_pairs(n, [&](int i, int j) {
-                    const float4 pi = t.pt[i], pj = t.pt[j];
-                    const bool lowc = (pi.x - pj.x) > gLf;        // certainly slope < L
-                    const bool highc = (pi.y - pj.y) < -gHf;      // certainly slope >= H
-                    if ((lowc || highc) && pi.z != pj.z) {
-                        below += lowc;
-                    } else {
-                        const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
-                        // the reference's value (_c_helper.pyx:371-376)
-                        const double sv = (de == 0.0) ? 1000.0 : dm / de;
-                        if (sv < L) ++below;
-                        else if (sv < H) {
-                            const unsigned int slot = atomicAdd(&t.nbuf, 1u);
-                            if (slot < TS_BUF) t.buf[slot] = sv;
-                        }
+                unsigned int n_under = 0, n_smp = 0;   // the underflow bin lives in a register
+                ts_for_cols(n, [&](int j) {
+                    const float4 pj = t.pt[j];
+                    const int jm = j % stride;
+                    int i = jm ? stride - jm : 0;
+                    for (; i < j; i += stride) {
+                        const float4 pi = t.pt[i];
+                        const float de = pi.x - pj.x;
+                        float sa = __fdividef(pi.y - pj.y, de);
+                        if (de == 0.0f) sa = 1000.0f;
+                        ++n_smp;
+                        n_under += sa < lo_f;
+                        if (sa >= lo_f && sa < hi_f)
+                            atomicAdd(&t.hist[min(TS_ABINS - 1, (int)((sa - lo_f) * inv_w)) + 1], 1u);
                     }
                 });
-                below = tb2_block_sum(below, sm);
+                n_under = tb2_block_sum(n_under, sm);
+                n_smp = tb2_block_sum(n_smp, sm);
+                if (tid == 0) t.hist[0] = n_under;
                 __syncthreads();
-                const long long nbuf = t.nbuf;
-                const long long kB = even ? k1 + 1 : k1;
-                if (nbuf <= TS_BUF && k1 >= (long long)below && kB < (long long)below + nbuf) {
-                    tb2_block_select2([&](int i) { return t.buf[i]; }, PredAll(), (int)nbuf,
-                                      (int)(k1 - (long long)below), even, &v1, &v2, sm);
-                    have = true;
-                    if (tid == 0) atomicAdd(&g_tb2_counters[1], 1ULL);
+                // sampled ranks that bracket the median ranks of the full set
+                long long kA, kB;
+                if (stride == 1) { kA = k1; kB = even ? k1 + 1 : k1; }
+                else {
+                    const long long kS = (long long)((double)k1 * (double)n_smp / (double)Np);
+                    const long long mg = (long long)(1.25 * sqrt((double)n_smp)) + 2;
+                    kA = kS - mg; kB = kS + mg;
                 }
+                if (tid == 0) { t.b1 = 0; t.b2 = TS_ABINS + 1; }   // "outside" unless located
+                __syncthreads();
+                if (kA >= 0 && kB < (long long)n_smp) {
+                    // bins holding the sampled ranks kA and kB: 256 threads x 17 bins
+                    const int per = (TS_ABINS + 2 + ST_THREADS - 1) / ST_THREADS;
+                    const int q0 = min(TS_ABINS + 2, tid * per), q1 = min(TS_ABINS + 2, q0 + per);
+                    unsigned int mine = 0;
+                    for (int q = q0; q < q1; ++q) mine += t.hist[q];
+                    const int lane = tid & 31, warp = tid >> 5;
+                    unsigned int inc = mine;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const unsigned int o = __shfl_up_sync(TB2_FULL_MASK, inc, off);
+                        if (lane >= off) inc += o;
+                    }
+                    if (lane == 31) sm.warp_tot[warp] = inc;
+                    __syncthreads();
+                    unsigned int base = 0;
+                    for (int q = 0; q < warp; ++q) base += sm.warp_tot[q];
+                    long long cum = (long long)base + inc - mine;
+                    for (int q = q0; q < q1; ++q) {
+                        const long long c = t.hist[q];
+                        if (kA >= cum && kA < cum + c) t.b1 = q;
+                        if (kB >= cum && kB < cum + c) t.b2 = q;
+                        cum += c;
+                    }
+                }
+                __syncthreads();
+                const int bA = (int)t.b1, bB = (int)t.b2;
+                if (bA >= 1 && bB <= TS_ABINS && bA <= bB) {
+                    // exact bracket with a one-bin margin on both sides
+                    const double L = (double)lo_f + (double)w_f * (double)(bA - 2);
+                    const double H = (double)lo_f + (double)w_f * (double)(bB + 1);
+                    // fp32 screen.  With Q_T(k) = md_k - T * ev_k, a pair a < b (ev_a <= ev_b)
+                    // has slope < T  <=>  Q_T(a) > Q_T(b)  and  slope >= T  <=>  Q_T(a) <= Q_T(b)
+                    // whenever ev_a != ev_b.  The fp32 images q = fma(-T_f, ev_f, md_f) carry an
+                    // absolute error <= 1.8e-7 * M * (1 + |T|) each (|values| <= M), so a
+                    // difference beyond g(T) = 1e-5 * M * (1 + |T|) settles the side of T with a
+                    // margin far above the 3 ulp between the exact quotient and the reference's
+                    // rounded one; anything closer, and every pair whose fp32 ev images
+                    // coincide (ev_a == ev_b gives the reference's 1000.0), takes the exact
+                    // fp64 path.
+                    const float M = fmaxf(1.0f, __uint_as_float(t.maxabs_bits));
+                    const float Lf = (float)L, Hf = (float)H;
+                    const float gLf = 1e-5f * M * (1.0f + fabsf(Lf)), gHf = 1e-5f * M * (1.0f + fabsf(Hf));
+                    __syncthreads();
+                    for (int i = tid; i < n; i += ST_THREADS) {
+                        const float ef = t.pt[i].x, mf = t.pt[i].y;
+                        t.pt[i] = make_float4(fmaf(-Lf, ef, mf), fmaf(-Hf, ef, mf), ef, 0.0f);
+                    }
+                    __syncthreads();     // hist is dead from here on: buf takes its place
+                    unsigned int below = 0;
+                    ts_for_cols(n, [&](int j) {
+                        const float4 pj = t.pt[j];
+                        const float xl = pj.x + gLf, yh = pj.y - gHf;
+#pragma unroll 4
+                        for (int i = 0; i < j; ++i) {
+                            const float4 pi = t.pt[i];
+                            const bool lowc = pi.x > xl;          // certainly slope < L
+                            const bool highc = pi.y < yh;         // certainly slope >= H
+                            if ((lowc || highc) && pi.z != pj.z) {
+                                below += lowc;
+                            } else {
+                                const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
+                                // the reference's value (_c_helper.pyx:371-376)
+                                const double sv = (de == 0.0) ? 1000.0 : dm / de;
+                                if (sv < L) ++below;
+                                else if (sv < H) {
+                                    const unsigned int slot = atomicAdd(&t.nbuf, 1u);
+                                    if (slot < TS_BUF) t.buf[slot] = sv;
+                                }
+                            }
+                        }
+                    });
+                    below = tb2_block_sum(below, sm);
+                    __syncthreads();
+                    const long long nbuf = t.nbuf;
+                    const long long kT = even ? k1 + 1 : k1;
+                    if (nbuf <= TS_BUF && k1 >= (long long)below && kT < (long long)below + nbuf) {
+                        tb2_block_select2([&](int i) { return t.buf[i]; }, PredAll(), (int)nbuf,
+                                          (int)(k1 - (long long)below), even, &v1, &v2, sm);
+                        have = true;
+                        if (tid == 0) atomicAdd(&g_tb2_counters[stride == 1 ? 1 : 4], 1ULL);
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
     if (!have && hs >= 16) {
