@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <memory>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../include/tombo_b200.h"
@@ -39,6 +40,7 @@ struct tb2_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;   // TB2_TRACE: upload bracket
     std::string err;
     int64_t launches = 0;
     double last_ms_total = 0, last_ms_dp = 0, last_dp_launches = 0, last_dp_reads = 0;
@@ -48,6 +50,7 @@ struct tb2_ctx {
     std::vector<tb2_ctx *> lanes;
     bool async_mode = false;       // upload / download do not synchronise
     int read_index_base = 0;       // first read of the chunk within the caller's batch
+    std::function<int()> after_first_launch;   // pipelined path: enqueue the next chunk's upload
     // model tables
     DevBuf model_means, model_sds, alt_means;
     int kmer_width = 0, central_pos = 0, alt_kmer_width = 0;

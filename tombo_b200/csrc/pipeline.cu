@@ -4,6 +4,9 @@
 // bandwidth; resquiggle.py:1492-1504, 1578-1588) is a host loop over kernel
 // launches on the whole batch; every kernel skips reads that are not active.
 #include "batch.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "kernels.h"
 #include <algorithm>
 #include <cmath>
@@ -330,8 +333,27 @@ extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, 
     cudaStream_t s = ctx->stream;
     const size_t esz = raw_dtype == 0 ? 8 : 2;
     TB2_CUDA_TRY(ctx, P[B_RAWIN].reserve((size_t)h->hb.total_s * esz + 8));
-    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_RAWIN].p, raw, (size_t)h->hb.total_s * esz, cudaMemcpyHostToDevice, s));
+    // the (small, possibly pageable) sequence copy goes first: a pageable source blocks the
+    // host until the copy has run, and behind the big signal copy that would serialise
+    // the pipelined path (H2D of chunk k+1 must overlap the kernels of chunk k)
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_SEQ].p, seq, (size_t)h->hb.total_seq, cudaMemcpyHostToDevice, s));
+    if (getenv("TB2_TRACE")) {
+        if (!ctx->ev_h0) { cudaEventCreate(&ctx->ev_h0); cudaEventCreate(&ctx->ev_h1); }
+        cudaEventRecord(ctx->ev_h0, s);
+    }
+    {
+        // in pieces: one monolithic DMA keeps the other lane's kernel launches waiting
+        // until it has drained
+        const size_t total = (size_t)h->hb.total_s * esz;
+        size_t piece = total;
+        if (const char *e = getenv("TB2_H2D_PIECE_MB")) piece = (size_t)atoll(e) << 20;
+        else if (ctx->async_mode) piece = (size_t)16 << 20;
+        if (piece == 0) piece = total;
+        for (size_t off = 0; off < total; off += piece)
+            TB2_CUDA_TRY(ctx, cudaMemcpyAsync((char *)P[B_RAWIN].p + off, (const char *)raw + off,
+                                              std::min(piece, total - off), cudaMemcpyHostToDevice, s));
+    }
+    if (ctx->ev_h1) cudaEventRecord(ctx->ev_h1, s);
     if (!ctx->async_mode) TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     h->uploaded = true;
     h->has_sv_in = h->has_stalls_in = false;
@@ -394,6 +416,11 @@ extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
     const int n = hb.n;
     auto &P = ctx->pool;
     cudaStream_t s = ctx->stream;
+    const bool trace = getenv("TB2_TRACE") != nullptr;
+    auto now_ms = [] {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double tc0 = now_ms();
     TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, s));
     TB2_CUDA_TRY(ctx, P[B_OUT_NORMMEAN].reserve((size_t)hb.total_b * 8 + 8));
     double *norm_sig_dev = nullptr;
@@ -430,8 +457,22 @@ extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
             if ((rc = run_call(ctx, v, p, sp, acfg, it == 0, norm_mean_dev, norm_sig_dev, rawdp_cap)))
                 return rc;
             if ((rc = tb2_launch_count_active(ctx, v, P[B_COUNTERS].as<int>()))) return rc;
-            TB2_CUDA_TRY(ctx, cudaMemcpyAsync(counters, P[B_COUNTERS].p, 8, cudaMemcpyDeviceToHost, s));
+            if (attempt == 0 && it == 0 && ctx->after_first_launch) {
+                auto fn = std::move(ctx->after_first_launch);
+                ctx->after_first_launch = nullptr;
+                if ((rc = fn())) return rc;
+            }
+            // read back through page-locked memory: a pageable destination would make the
+            // driver stage the copy and stall behind the other lane's bulk transfers
+            if (!ctx->pinned) {
+                TB2_CUDA_TRY(ctx, cudaHostAlloc(&ctx->pinned, 256, cudaHostAllocPortable));
+                ctx->pinned_cap = 256;
+            }
+            const double th0 = trace ? now_ms() : 0;
+            TB2_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, P[B_COUNTERS].p, 8, cudaMemcpyDeviceToHost, s));
             TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            memcpy(counters, ctx->pinned, 8);
+            if (trace) fprintf(stderr, "[tb2]   call %d.%d: enqueued at +%.2f ms, synced at +%.2f ms\n", attempt, it, th0 - tc0, now_ms() - tc0);
             float ms = 0;
             if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) {
                 ms_dp += ms; ++dp_launches; dp_reads += active_now;
@@ -554,16 +595,23 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
     }
     const int K = ctx->kmer_width;
     const int n = (int)n_reads;
-    const int n_chunks = (int)((n_reads + CH - 1) / CH);
+    // chunk starts: a short first chunk (its upload is the only exposed one), then full
+    // chunks of 4 reads per resident DP warp, the remainder last (short result tail)
+    std::vector<int> cstart;
+    {
+        int64_t at = 0;
+        const int64_t ramp[2] = {CH / 4, CH / 2};
+        for (int q = 0; q < 2 && n_reads - at > CH; ++q) { cstart.push_back((int)at); at += ramp[q]; }
+        while (at < n_reads) { cstart.push_back((int)at); at += CH; }
+        cstart.push_back((int)n_reads);
+    }
+    const int n_chunks = (int)cstart.size() - 1;
     std::vector<int64_t> base_off((size_t)n + 1, 0);
     for (int r = 0; r < n; ++r)
         base_off[r + 1] = base_off[r] + std::max<int64_t>(0, (seq_off[r + 1] - seq_off[r]) - (K - 1));
     std::vector<std::vector<int64_t>> ro((size_t)n_chunks), so((size_t)n_chunks);
     const size_t esz = raw_dtype == 0 ? 8 : 2;
-    auto bounds = [&](int k, int *a, int *b) {
-        *a = (int)((int64_t)n * k / n_chunks);
-        *b = (int)((int64_t)n * (k + 1) / n_chunks);
-    };
+    auto bounds = [&](int k, int *a, int *b) { *a = cstart[k]; *b = cstart[k + 1]; };
     auto upload = [&](int k) -> int {
         int a, b;
         bounds(k, &a, &b);
@@ -576,14 +624,35 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
                                 ro[k].data(), seq + seq_off[a], so[k].data(), params, policy);
     };
     double ms_total = 0, ms_dp = 0, dp_launches = 0, dp_reads = 0;
+    const bool trace = getenv("TB2_TRACE") != nullptr;
+    auto now_ms = [] {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double t00 = now_ms();
     rc = upload(0);
     for (int k = 0; k < n_chunks && rc == TB2_OK; ++k) {
         int a, b;
         bounds(k, &a, &b);
         tb2_ctx *ln = ctx->lanes[k & 1];
-        if (k + 1 < n_chunks && (rc = upload(k + 1))) break;
+        const double t0 = now_ms();
+        // the next chunk's upload is enqueued from inside compute(), right after this
+        // chunk's first kernels: work submitted behind a bulk copy (even on another
+        // stream) was observed to wait for it, work submitted ahead of it overlaps
+        if (k + 1 < n_chunks) ln->after_first_launch = [&upload, k]() { return upload(k + 1); };
+        const double t1 = now_ms();
         ln->read_index_base = a;
-        if ((rc = tb2_batch_compute(ln, params, save_params, policy, norm_signal != nullptr))) break;
+        rc = tb2_batch_compute(ln, params, save_params, policy, norm_signal != nullptr);
+        ln->after_first_launch = nullptr;
+        if (rc) break;
+        if (trace && ln->ev_h0) {
+            float h2d = 0, gap = 0;
+            cudaEventElapsedTime(&h2d, ln->ev_h0, ln->ev_h1);
+            cudaEventElapsedTime(&gap, ln->ev_h1, ln->ev0);
+            fprintf(stderr, "[tb2]   own H2D took %.2f ms, ended %.2f ms before compute began on the device\n", h2d, gap);
+        }
+        if (trace)
+            fprintf(stderr, "[tb2] chunk %d: t=%.1f upload(k+1) %.2f ms, compute %.2f ms (device %.2f)\n", k,
+                    t0 - t00, t1 - t0, now_ms() - t1, ln->last_ms_total);
         ms_total += ln->last_ms_total; ms_dp += ln->last_ms_dp;
         dp_launches += ln->last_dp_launches; dp_reads += ln->last_dp_reads;
         rc = tb2_batch_download(ln, segs + base_off[a] + a, read_start_rel_to_raw + a, scale_out + a,
