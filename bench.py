@@ -399,7 +399,10 @@ def main():
         tp = os.path.join(REPO, 'profiles', 'k_align_traffic.json')
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+                # measured DRAM bytes per read of the captured launch x reads of an average
+                # launch of this run (per launch, like `achieved`)
+                traffic = (json.load(open(tp)).get('dram_bytes_per_read')
+                           * dp_reads / max(1.0, dp_launches))
             except Exception:
                 traffic = None
         line = {
