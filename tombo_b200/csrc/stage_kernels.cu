@@ -817,7 +817,7 @@ struct TsSmem {
         unsigned int hist[TS_ABINS + 2];   // also holds the TS_BINS + 2 exact bins
         double buf[TS_BUF];                // bracket sample, then the slopes inside the bracket
     };
-    unsigned int nbuf, b1, b2, below, maxabs_bits;
+    unsigned int nbuf, nout, b1, b2, below, maxabs_bits;
     int ok;
 };
 
@@ -1046,7 +1046,12 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                         t.pt[i] = make_float4(fmaf(-Lf, ef, mf), fmaf(-Hf, ef, mf), ef, 0.0f);
                     }
                     __syncthreads();     // hist is dead from here on: buf takes its place
+                    // screened pairs are settled in registers; the others (inside the
+                    // bracket or within the guard) are queued as (i, j) and evaluated
+                    // afterwards by all threads, so the fp64 divide never runs divergent
                     unsigned int below = 0;
+                    unsigned int *queue = reinterpret_cast<unsigned int *>(t.buf);
+                    const unsigned int QCAP = 2 * TS_BUF;
                     ts_for_cols(n, [&](int j) {
                         const float4 pj = t.pt[j];
                         const float xl = pj.x + gLf, yh = pj.y - gHf;
@@ -1058,23 +1063,35 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                             if ((lowc || highc) && pi.z != pj.z) {
                                 below += lowc;
                             } else {
-                                const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
-                                // the reference's value (_c_helper.pyx:371-376)
-                                const double sv = (de == 0.0) ? 1000.0 : dm / de;
-                                if (sv < L) ++below;
-                                else if (sv < H) {
-                                    const unsigned int slot = atomicAdd(&t.nbuf, 1u);
-                                    if (slot < TS_BUF) t.buf[slot] = sv;
-                                }
+                                const unsigned int slot = atomicAdd(&t.nbuf, 1u);
+                                if (slot < QCAP) queue[slot] = ((unsigned int)i << 16) | (unsigned int)j;
                             }
                         }
                     });
+                    __syncthreads();
+                    const unsigned int nq = t.nbuf;
+                    double *outv = reinterpret_cast<double *>(t.pt);   // pt is dead now
+                    if (tid == 0) t.nout = 0;
+                    __syncthreads();
+                    if (nq <= QCAP) {
+                        for (unsigned int q = tid; q < nq; q += ST_THREADS) {
+                            const int i = (int)(queue[q] >> 16), j = (int)(queue[q] & 0xffffu);
+                            const double de = t.ev[i] - t.ev[j], dm = t.md[i] - t.md[j];
+                            // the reference's value (_c_helper.pyx:371-376)
+                            const double sv = (de == 0.0) ? 1000.0 : dm / de;
+                            if (sv < L) ++below;
+                            else if (sv < H) {
+                                const unsigned int slot = atomicAdd(&t.nout, 1u);
+                                if (slot < TS_BUF) outv[slot] = sv;
+                            }
+                        }
+                    }
                     below = tb2_block_sum(below, sm);
                     __syncthreads();
-                    const long long nbuf = t.nbuf;
+                    const long long nbuf = t.nout;
                     const long long kT = even ? k1 + 1 : k1;
-                    if (nbuf <= TS_BUF && k1 >= (long long)below && kT < (long long)below + nbuf) {
-                        tb2_block_select2([&](int i) { return t.buf[i]; }, PredAll(), (int)nbuf,
+                    if (nq <= QCAP && nbuf <= TS_BUF && k1 >= (long long)below && kT < (long long)below + nbuf) {
+                        tb2_block_select2([&](int i) { return outv[i]; }, PredAll(), (int)nbuf,
                                           (int)(k1 - (long long)below), even, &v1, &v2, sm);
                         have = true;
                         if (tid == 0) atomicAdd(&g_tb2_counters[stride == 1 ? 1 : 4], 1ULL);
