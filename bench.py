@@ -26,6 +26,11 @@ import sys
 import threading
 import time
 
+# the CPU arms run one single-threaded worker process per host thread (the reference's
+# --processes model): keep BLAS / OpenMP pools from oversubscribing the cores
+for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+    os.environ.setdefault(_v, '1')
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -218,17 +223,27 @@ def cpu_baseline_kind():
     return 'port'
 
 
-def run_cpu(n_reads, cores, kind, seed0=900000):
+def cpu_pool(cores, kind):
+    import multiprocessing as mp
+    pool = mp.get_context('fork').Pool(cores, initializer=_cpu_init, initargs=(kind,))
+    pool.map(_cpu_one, range(899000, 899000 + cores))            # import + warm-up
+    return pool
+
+
+def run_cpu(n_reads, cores, kind, seed0=900000, pool=None):
     """reads/s of the CPU implementation with `cores` worker processes
     (multiprocessing.Pool == the compute half of the reference's --processes)."""
-    import multiprocessing as mp
-    ctx = mp.get_context('fork')
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(kind,)) as pool:
-        pool.map(_cpu_one, range(seed0, seed0 + cores))          # import + warm-up
+    own = pool is None
+    if own:
+        pool = cpu_pool(cores, kind)
+    try:
         t0 = time.perf_counter()
         out = pool.map(_cpu_one, range(seed0 + cores, seed0 + cores + n_reads),
                        chunksize=max(1, n_reads // (cores * 8)))
         wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close(); pool.join()
     samples = sum(o[1] for o in out)
     return {'reads_per_s': n_reads / wall, 'samples_per_s': samples / wall, 'wall_s': wall,
             'ok': sum(o[2] for o in out), 'n': n_reads,
@@ -295,11 +310,13 @@ def main():
             return
         kind = cpu_baseline_kind()
         n = args.cpu_sample or cores * 24
+        pool = cpu_pool(cores, kind)
         for _ in range(max(0, args.warmup - 1)):
-            run_cpu(cores * 2, cores, kind)
+            run_cpu(cores * 2, cores, kind, pool=pool)
         t0 = time.perf_counter()
-        rs = [run_cpu(n, cores, kind, seed0=910000 + 7919 * i) for i in range(args.steps)]
+        rs = [run_cpu(n, cores, kind, seed0=910000 + 7919 * i, pool=pool) for i in range(args.steps)]
         wall = time.perf_counter() - t0
+        pool.close(); pool.join()
         rps = sum(r['n'] for r in rs) / sum(r['wall_s'] for r in rs)
         sps = sum(r['samples_per_s'] * r['wall_s'] for r in rs) / sum(r['wall_s'] for r in rs)
         line = {
