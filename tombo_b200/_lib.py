@@ -195,7 +195,8 @@ class Context(object):
                       C.byref(p), C.byref(policy)))
         k = self.kmer_width
         n = raw_off.shape[0] - 1
-        nb = (seq_off[1:] - seq_off[:-1]) - (k - 1)
+        # sequences shorter than the k-mer map zero bases (the library clamps the same way)
+        nb = np.maximum((seq_off[1:] - seq_off[:-1]) - (k - 1), 0)
         self._base_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
         self._seg_off = self._base_off + np.arange(n + 1, dtype=np.int64)
         self._n_samples = int(raw_off[-1])
@@ -490,7 +491,8 @@ class Context(object):
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         n = raw_off.shape[0] - 1
         k = self.kmer_width
-        nb = (seq_off[1:] - seq_off[:-1]) - (k - 1)
+        # sequences shorter than the k-mer map zero bases (the library clamps the same way)
+        nb = np.maximum((seq_off[1:] - seq_off[:-1]) - (k - 1), 0)
         base_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
         seg_off = base_off + np.arange(n + 1, dtype=np.int64)
         if out is None:

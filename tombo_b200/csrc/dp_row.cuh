@@ -846,7 +846,7 @@ __device__ __noinline__ int tb2_tb_seg_wf(const uint32_t *tbw, long long total_w
             uint32_t code;
             for (;;) {
                 const int ts = bp + toff;
-                const int wi = ts >> 4, rel = wi - bs;
+                const int wi = ts >> 4, rel = wi - bs, q = ts & 15;
                 uint32_t v;
                 if (rel >= 0 && rel < 3) {
                     const uint32_t mine = rel == 0 ? w0 : (rel == 1 ? w1 : w2);
@@ -854,9 +854,16 @@ __device__ __noinline__ int tb2_tb_seg_wf(const uint32_t *tbw, long long total_w
                 } else {
                     v = tbs[wi * 32 + k];
                 }
-                code = (v >> (2 * (ts & 15))) & 3u;
-                if (code != 0u) break;
-                --bp;
+                // a run of stays (code 0) is skipped in one go: highest non-zero move at
+                // or below position q of this word
+                const uint32_t nz = ((v | (v >> 1)) & 0x55555555u) & (0xffffffffu >> (30 - 2 * q));
+                if (nz != 0u) {
+                    const int kq = (31 - __clz(nz)) >> 1;
+                    bp -= q - kq;
+                    code = (v >> (2 * kq)) & 3u;
+                    break;
+                }
+                bp -= q + 1;
                 if (bp < 0) return TB2_ERR_UNEXPECTED;
             }
             if (code == 2u) --bp;

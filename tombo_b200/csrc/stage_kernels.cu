@@ -190,6 +190,54 @@ __device__ __forceinline__ bool cand_gt(double si, int i, double sk, int k)
     return si > sk || (si == sk && i > k);
 }
 
+// np.cumsum(concatenate([[0.0], signal])) (_c_helper.pyx:93-94): strictly sequential
+// fp64 sums, one warp per read.  The warp stages 256 samples in shared memory
+// (coalesced), then every lane carries the same running sum through them (broadcast
+// reads issued ahead of the adds, so the serial chain is the add latency alone); lane
+// k keeps the prefix sums of elements k, k + 32, ... for a coalesced store.
+#define CS_WARPS 4
+__global__ void __launch_bounds__(CS_WARPS * 32, 8)
+k_cumsum(BatchView b, int on_raw)
+{
+    __shared__ double s_all[CS_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * CS_WARPS + warp;
+    if (r >= b.n_reads) return;
+    if (!rd_active(b.st[r])) return;
+    double *s_x = s_all[warp];
+    const long long ro = b.raw_off[r];
+    const int n = (int)(b.raw_off[r + 1] - ro);
+    const double *sig = (on_raw ? b.rawf : b.norm) + ro;
+    double *cs = b.cs + ro + r;
+    double acc = 0.0;
+    if (lane == 0) cs[0] = 0.0;
+    for (int base = 0; base < n; base += 256) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = base + q * 32 + lane;
+            s_x[q * 32 + lane] = (i < n) ? sig[i] : 0.0;
+        }
+        __syncwarp();
+        double mine[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double m_q = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                acc = acc + s_x[q * 32 + k];
+                if (lane == k) m_q = acc;
+            }
+            mine[q] = m_q;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = base + q * 32 + lane;
+            if (i < n) cs[i + 1] = mine[q];
+        }
+    }
+}
+
 // bit i of word w <-> candidate 32 w + i.  X(i + o) / X(i - o) as words aligned to i.
 __device__ __forceinline__ uint32_t cp_shr(const uint32_t *x, int w, int nw, int o)
 {
@@ -209,7 +257,6 @@ k_cpts(BatchView b, tb2_params p, int on_raw, int smem_words)
 {
     extern __shared__ uint32_t cp_smem[];
     __shared__ SelectSmem sm;
-    __shared__ double s_x[256];
     __shared__ int s_pos;
     const int r = blockIdx.x;
     ReadState &s = b.st[r];
@@ -227,41 +274,7 @@ k_cpts(BatchView b, tb2_params p, int on_raw, int smem_words)
         n_cand = n + 1 - 2 * w;
         bound = n_cand - 2 * w;  // num_cands = candidate_poss.shape[0] - 2*w (:105-106)
         if (n_cand <= 0) { if (tid == 0) s.status = TB2_ERR_UNEXPECTED; return; }
-        // np.cumsum(concatenate([[0.0], signal])): strictly sequential fp64 sums.
-        // One warp stages 256 samples in shared memory (coalesced), then every lane
-        // carries the same running sum through them (broadcast reads issued ahead of
-        // the adds, so the serial chain is the add latency alone); lane k keeps the
-        // prefix sums of elements k, k + 32, ... for a coalesced store.
-        if (tid < 32) {
-            double acc = 0.0;
-            if (tid == 0) cs[0] = 0.0;
-            for (int base = 0; base < n; base += 256) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int i = base + q * 32 + tid;
-                    s_x[q * 32 + tid] = (i < n) ? sig[i] : 0.0;
-                }
-                __syncwarp();
-                double mine[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    double m_q = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        acc = acc + s_x[q * 32 + k];
-                        if (tid == k) m_q = acc;
-                    }
-                    mine[q] = m_q;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int i = base + q * 32 + tid;
-                    if (i < n) cs[i + 1] = mine[q];
-                }
-            }
-        }
-        __syncthreads();
+        // cs = np.cumsum(concatenate([[0.0], signal])) comes from k_cumsum
         for (int i = tid; i < n_cand; i += ST_THREADS)
             sc[i] = fabs(((2 * cs[i + w]) - cs[i]) - cs[i + 2 * w]);   // :95-98
     } else {
@@ -1271,6 +1284,10 @@ int tb2_launch_cpts(tb2_ctx *ctx, const BatchView &b, const tb2_params &p, int o
 {
     // bit sets of the greedy pass: 4 + (min_obs_per_base - 1) words per 32 candidates, in
     // shared memory when the longest read of the batch fits (else the read's scratch)
+    if (!p.use_t_test_seg) {
+        k_cumsum<<<(b.n_reads + CS_WARPS - 1) / CS_WARPS, CS_WARPS * 32, 0, ctx->stream>>>(b, on_raw);
+        TB2_CHECK_LAUNCH(ctx);
+    }
     const long long nw = (b.max_raw + 32) / 32;
     long long words = (4 + std::max(0, (int)p.min_obs_per_base - 1)) * nw;
     if (words * 4 > 64 * 1024) words = 0;
