@@ -12,7 +12,7 @@
 // (find_adaptive_base_assignment resquiggle.py:986-989): wavefront engine only, so
 // fewer registers and twice the resident warps of the general kernel.
 template <int KLASS>
-__global__ void __launch_bounds__(ALIGN_WARPS * 32, (KLASS == 1) ? 6 : 4)
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, (KLASS == 1) ? 8 : 4)
 k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, int *counter)
 {
     extern __shared__ double smem[];

@@ -564,7 +564,7 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
         (raw_dtype != 0 && raw_dtype != 1) || n_reads > 0x7ffffff0)
         return TB2_ERR_INVALID_ARG;
     // chunk = 4 reads per resident DP warp of the lean kernel
-    const int64_t CH = (int64_t)4 * ctx->sm_count * 24;
+    const int64_t CH = (int64_t)4 * ctx->sm_count * 32;
     if (n_reads <= CH + CH / 2) {
         rc = tb2_batch_upload(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy);
         if (rc) return rc;

@@ -28,8 +28,8 @@ struct SelectSmem {
     unsigned long long red_u64[8], red_and[8];
     unsigned int red_u32[8];
     unsigned long long small[TB2_SEL_SMALL];   // finishing list of the radix select
-    unsigned long long result;
-    unsigned int n_small;
+    unsigned long long result, result2;   // rank k; rank k + 1 when it sat in the same list
+    unsigned int n_small, have2;
 };
 
 // block-wide sum of an unsigned (all threads get the result)
@@ -73,6 +73,7 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
     unsigned long long prefix = 0, mask = 0;
     unsigned int kk = (unsigned int)k;
     const int tid = threadIdx.x;
+    if (tid == 0) sm.have2 = 0u;     // published by the barriers below
     // digits shared by every key need no pass: start below the common leading bytes
     int shift0 = 56;
     {
@@ -157,6 +158,7 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
                     rank += (o < mine) || (o == mine && q < (unsigned int)tid);
                 }
                 if (rank == kk) sm.result = mine;
+                if (rank == kk + 1u) { sm.result2 = mine; sm.have2 = 1u; }
             }
             __syncthreads();
             const unsigned long long res = sm.result;
@@ -176,6 +178,11 @@ __device__ void tb2_block_select2(F f, Pred pred, int n, int k, bool want2, doub
     *v0 = tb2_unkey(K);
     *v1 = *v0;
     if (!want2) return;
+    // the finishing list usually holds rank k + 1 as well
+    const unsigned int h2 = sm.have2;
+    const unsigned long long r2 = sm.result2;
+    __syncthreads();
+    if (h2) { *v1 = tb2_unkey(r2); return; }
     unsigned int cnt_le = 0;
     unsigned long long min_gt = ~0ULL;
     for (int i = threadIdx.x; i < n; i += TB2_SEL_THREADS) {

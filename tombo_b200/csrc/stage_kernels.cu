@@ -1065,22 +1065,38 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                     unsigned int below = 0;
                     unsigned int *queue = reinterpret_cast<unsigned int *>(t.buf);
                     const unsigned int QCAP = 2 * TS_BUF;
-                    ts_for_cols(n, [&](int j) {
-                        const float4 pj = t.pt[j];
-                        const float xl = pj.x + gLf, yh = pj.y - gHf;
+                    auto push = [&](int i, int j) {
+                        const unsigned int slot = atomicAdd(&t.nbuf, 1u);
+                        if (slot < QCAP) queue[slot] = ((unsigned int)i << 16) | (unsigned int)j;
+                    };
+                    {
+                        // thread c owns columns ja = c and jb = n - 1 - c (ja <= jb): rows
+                        // i < ja are tested against both with one load of point i
+                        const int half = (n + 1) / 2;
+                        for (int cidx = tid; cidx < half; cidx += ST_THREADS) {
+                            const int ja = cidx, jb = n - 1 - cidx;
+                            const float4 pa = t.pt[ja], pb = t.pt[jb];
+                            const float xla = pa.x + gLf, yha = pa.y - gHf;
+                            const float xlb = pb.x + gLf, yhb = pb.y - gHf;
+                            int i = 0;
+                            if (ja != jb) {
 #pragma unroll 4
-                        for (int i = 0; i < j; ++i) {
-                            const float4 pi = t.pt[i];
-                            const bool lowc = pi.x > xl;          // certainly slope < L
-                            const bool highc = pi.y < yh;         // certainly slope >= H
-                            if ((lowc || highc) && pi.z != pj.z) {
-                                below += lowc;
-                            } else {
-                                const unsigned int slot = atomicAdd(&t.nbuf, 1u);
-                                if (slot < QCAP) queue[slot] = ((unsigned int)i << 16) | (unsigned int)j;
+                                for (; i < ja; ++i) {
+                                    const float4 pi = t.pt[i];
+                                    const bool la = pi.x > xla, ha = pi.y < yha;
+                                    const bool lb = pi.x > xlb, hb = pi.y < yhb;
+                                    if ((la || ha) && pi.z != pa.z) below += la; else push(i, ja);
+                                    if ((lb || hb) && pi.z != pb.z) below += lb; else push(i, jb);
+                                }
+                            }
+#pragma unroll 4
+                            for (; i < jb; ++i) {
+                                const float4 pi = t.pt[i];
+                                const bool lb = pi.x > xlb, hb = pi.y < yhb;
+                                if ((lb || hb) && pi.z != pb.z) below += lb; else push(i, jb);
                             }
                         }
-                    });
+                    }
                     __syncthreads();
                     const unsigned int nq = t.nbuf;
                     double *outv = reinterpret_cast<double *>(t.pt);   // pt is dead now
