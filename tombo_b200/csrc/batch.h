@@ -35,6 +35,7 @@ struct BatchView {
     int kmer_width;
     int max_raw;       // longest raw signal of the batch (samples)
     const long long *raw_off, *seq_off, *base_off, *ev_off;
+    const int *order;  // reads by descending raw length (launch order), null = index order
     const unsigned char *seq;
     double *rawf;      // raw signal as fp64 (reversed for RNA)          [sum S]
     double *norm;      // normalised signal of the current call         [sum S]

@@ -30,6 +30,7 @@ k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, 
         if (lane == 0) r = atomicAdd(counter, 1);
         r = __shfl_sync(TB2_FULL_MASK, r, 0);
         if (r >= b.n_reads) break;
+        if (b.order) r = b.order[r];
         const size_t ix = (size_t)r * b.stride;
         if (b.status[ix] != TB2_OK) continue;
         if (b.active && !b.active[ix]) continue;
@@ -408,6 +409,7 @@ extern "C" int tb2_find_adaptive_base_assignment(
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[S_G].p, small, 32, cudaMemcpyHostToDevice, s));
     AlignBatch b;
     b.n_reads = 1;
+    b.order = nullptr;
     b.cpts = P[S_A].as<int>();
     b.em = P[S_B].as<double>();
     b.ev_off = P[S_E].as<long long>();

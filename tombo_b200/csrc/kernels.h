@@ -9,6 +9,7 @@
 //   read_tb/segs   at base_off[r] + r   (nb + 1 entries)
 struct AlignBatch {
     int n_reads;
+    const int *order;   // work order (longest first), null = index order
     const int *cpts;
     const double *em;
     const long long *ev_off;

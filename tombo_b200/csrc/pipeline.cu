@@ -24,7 +24,7 @@ enum {
     B_RAWOFF = 12, B_SEQOFF, B_BASEOFF, B_EVOFF, B_SEQ, B_RAWIN, B_RAWF, B_NORM, B_CS, B_SCORES,
     B_CSTATE, B_CPTS, B_EM, B_RM, B_RS, B_BM, B_TMPB, B_STARTS, B_READTB, B_SEGSDP, B_SEGS,
     B_STALLS, B_STATE, B_DBG, B_COUNTERS, B_OUT_SEGS, B_OUT_NORMMEAN, B_OUT_NORMSIG, B_OUT_SMALL,
-    B_SVIN, B_NSTALL
+    B_SVIN, B_NSTALL, B_ORDER
 };
 
 // optional caller-provided per-read inputs of resquiggle_read: map_res.scale_values
@@ -105,6 +105,24 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_SEQOFF].p, seq_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_BASEOFF].p, hb.base_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_EVOFF].p, hb.ev_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    // launch order: longest reads first, so that the persistent DP warps and the
+    // CTA-per-read kernels do not end on a straggler (length bucketing of mixed batches)
+    v.order = nullptr;
+    {
+        long long mn = max_raw;
+        for (int r = 0; r < n; ++r) mn = std::min<long long>(mn, raw_off[r + 1] - raw_off[r]);
+        if (mn != max_raw && n > 1) {
+            std::vector<int> order((size_t)n);
+            for (int r = 0; r < n; ++r) order[r] = r;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                return raw_off[a + 1] - raw_off[a] > raw_off[b + 1] - raw_off[b];
+            });
+            TB2_CUDA_TRY(ctx, P[B_ORDER].reserve((size_t)n * 4));
+            TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_ORDER].p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+            TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // order is a local
+            v.order = P[B_ORDER].as<int>();
+        }
+    }
     v.n_reads = n;
     v.kmer_width = K;
     v.raw_off = P[B_RAWOFF].as<long long>();
@@ -220,6 +238,7 @@ AlignBatch make_align_batch(tb2_ctx *ctx, const BatchView &v, const tb2_params &
 {
     AlignBatch ab;
     ab.n_reads = v.n_reads;
+    ab.order = v.order;
     ab.cpts = v.cpts; ab.em = v.em; ab.ev_off = v.ev_off;
     ab.rm = v.rm; ab.rs = v.rs; ab.base_off = v.base_off;
     ab.starts = v.starts; ab.read_tb = v.read_tb; ab.segs = v.segs_dp;

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(ST_THREADS)
 k_normalize(BatchView b, StagePolicy pol, int first_call)
 {
     __shared__ SelectSmem sm;
-    const int r = blockIdx.x;
+    const int r = b.order ? b.order[blockIdx.x] : blockIdx.x;
     ReadState &s = b.st[r];
     if (!rd_active(s)) return;
     const long long ro = b.raw_off[r];
@@ -258,7 +258,7 @@ k_cpts(BatchView b, tb2_params p, int on_raw, int smem_words)
     extern __shared__ uint32_t cp_smem[];
     __shared__ SelectSmem sm;
     __shared__ int s_pos;
-    const int r = blockIdx.x;
+    const int r = b.order ? b.order[blockIdx.x] : blockIdx.x;
     ReadState &s = b.st[r];
     if (!rd_active(s)) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -883,7 +883,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
     extern __shared__ unsigned char ts_raw[];
     TsSmem &t = *reinterpret_cast<TsSmem *>(ts_raw);
     __shared__ SelectSmem sm;
-    const int r = blockIdx.x;
+    const int r = b.order ? b.order[blockIdx.x] : blockIdx.x;
     ReadState &s = b.st[r];
     if (!rd_active(s)) return;
     const int tid = threadIdx.x;
