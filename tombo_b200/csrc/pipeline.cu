@@ -582,9 +582,10 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
         !read_start_rel_to_raw || !scale_out || !sig_match_score || !status || !n_iters || !flags ||
         (raw_dtype != 0 && raw_dtype != 1) || n_reads > 0x7ffffff0)
         return TB2_ERR_INVALID_ARG;
-    // chunk = 4 reads per resident DP warp of the lean kernel
-    const int64_t CH = (int64_t)4 * ctx->sm_count * 32;
-    if (n_reads <= CH + CH / 2) {
+    // chunk sizes in units of one read per resident DP warp of the lean kernel
+    const int64_t U = (int64_t)ctx->sm_count * 32;
+    const int64_t CH = 8 * U;
+    if (n_reads <= 6 * U) {
         rc = tb2_batch_upload(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy);
         if (rc) return rc;
         if ((rc = tb2_batch_compute(ctx, params, save_params, policy, norm_signal != nullptr))) return rc;
@@ -614,13 +615,14 @@ extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *r
     }
     const int K = ctx->kmer_width;
     const int n = (int)n_reads;
-    // chunk starts: a short first chunk (its upload is the only exposed one), then full
-    // chunks of 4 reads per resident DP warp, the remainder last (short result tail)
+    // chunk starts: short first chunks (the first upload is the only exposed one), then
+    // chunks of 8 reads per resident DP warp (few launches, short tails), the remainder
+    // last
     std::vector<int> cstart;
     {
         int64_t at = 0;
-        const int64_t ramp[2] = {CH / 4, CH / 2};
-        for (int q = 0; q < 2 && n_reads - at > CH; ++q) { cstart.push_back((int)at); at += ramp[q]; }
+        const int64_t ramp[2] = {2 * U, 4 * U};
+        for (int q = 0; q < 2 && n_reads - at > ramp[q]; ++q) { cstart.push_back((int)at); at += ramp[q]; }
         while (at < n_reads) { cstart.push_back((int)at); at += CH; }
         cstart.push_back((int)n_reads);
     }
