@@ -80,7 +80,43 @@ class ClockSampler(object):
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self):
+        """NVML in-process (tens of samples per timed region); False if unavailable"""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.device
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.device])
+                except Exception:
+                    idx = self.device
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(h))
+                rec = [sm, mx, 'Not Active', 'Not Active', 'Not Active', 'Not Active']
+                for bit, pos in bits:
+                    if r & bit:
+                        rec[pos] = 'Active'
+                self.samples.append(tuple(rec))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
