@@ -77,28 +77,47 @@ class ClockSampler(object):
     def __init__(self, device):
         self.device = device
         self.samples = []
+        self.err = ''
+        self._nvml = self._nvml_open()
         self._stop = threading.Event()
         self._t = None
 
+    def _nvml_open(self):
+        """NVML handle of this rank's GPU (opened before the timed region); None if unavailable"""
+        for attempt in range(3):
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+                h = None
+                if vis:
+                    ents = [e.strip() for e in vis.split(',')]
+                    ent = ents[self.device] if self.device < len(ents) else ''
+                    try:
+                        h = nv.nvmlDeviceGetHandleByIndex(int(ent))
+                    except Exception:
+                        try:
+                            h = nv.nvmlDeviceGetHandleByUUID(ent.encode())
+                        except Exception:
+                            h = None
+                if h is None:
+                    h = nv.nvmlDeviceGetHandleByIndex(self.device)
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+                get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                    getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+                nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                get_reasons(h)
+                return nv, h, mx, get_reasons
+            except Exception as e:
+                self.err = 'nvml: %r' % (e,)
+                time.sleep(0.05 * (attempt + 1))
+        return None
+
     def _run_nvml(self):
         """NVML in-process (tens of samples per timed region); False if unavailable"""
-        try:
-            import pynvml as nv
-            nv.nvmlInit()
-            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
-            idx = self.device
-            if vis:
-                try:
-                    idx = int(vis.split(',')[self.device])
-                except Exception:
-                    idx = self.device
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
-                getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
-            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-        except Exception:
+        if self._nvml is None:
             return False
+        nv, h, mx, get_reasons = self._nvml
         bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
         while not self._stop.is_set():
             try:
@@ -109,10 +128,10 @@ class ClockSampler(object):
                     if r & bit:
                         rec[pos] = 'Active'
                 self.samples.append(tuple(rec))
-            except Exception:
-                pass
+            except Exception as e:
+                self.err = 'nvml sample: %r' % (e,)
             self._stop.wait(0.02)
-        return True
+        return bool(self.samples)
 
     def _run(self):
         if self._run_nvml():
@@ -127,8 +146,8 @@ class ClockSampler(object):
                                    text=True, timeout=5).stdout.strip().split('\n')[0]
                 f = [x.strip() for x in o.split(',')]
                 self.samples.append((float(f[0]), float(f[1]), f[2], f[3], f[4], f[5]))
-            except Exception:
-                pass
+            except Exception as e:
+                self.err += ' nvidia-smi: %r' % (e,)
             self._stop.wait(0.2)
 
     def start(self):
@@ -140,7 +159,7 @@ class ClockSampler(object):
         if self._t:
             self._t.join(timeout=6)
         if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable'], 'error': self.err[:300]}
         sm = sorted(s[0] for s in self.samples)
         reasons = []
         for name, idx in (('hw_slowdown', 2), ('hw_thermal_slowdown', 3),
