@@ -5,6 +5,8 @@
 // launches on the whole batch; every kernel skips reads that are not active.
 #include "batch.h"
 #include <chrono>
+#include <exception>
+#include <string>
 #include <cstdio>
 #include <cstdlib>
 #include "kernels.h"
@@ -61,7 +63,8 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
         const long long s = raw_off[r + 1] - raw_off[r];
         long long nb = (seq_off[r + 1] - seq_off[r]) - (K - 1);
         if (nb < 0) nb = 0;
-        if (s < 0 || s > 0x3fffffff || nb > 0x3fffffff) return TB2_ERR_INVALID_ARG;
+        if (s < 0 || s > 0x3fffffff || nb > 0x3fffffff || seq_off[r + 1] < seq_off[r])
+            return TB2_ERR_INVALID_ARG;
         hb.base_off[r + 1] = hb.base_off[r] + nb;
         hb.ev_off[r + 1] = hb.ev_off[r] + std::max<long long>(2, num_events_of(s, nb, p, ratio)) + 1;
     }
@@ -330,7 +333,7 @@ BatchHolder *holder_of(tb2_ctx *ctx)
 }
 }  // namespace
 
-extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
+static int batch_upload_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
                                 const int64_t *raw_off, const uint8_t *seq, const int64_t *seq_off,
                                 const tb2_params *params, const tb2_policy *policy)
 {
@@ -360,18 +363,7 @@ extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, 
         if (!ctx->ev_h0) { cudaEventCreate(&ctx->ev_h0); cudaEventCreate(&ctx->ev_h1); }
         cudaEventRecord(ctx->ev_h0, s);
     }
-    {
-        // in pieces: one monolithic DMA keeps the other lane's kernel launches waiting
-        // until it has drained
-        const size_t total = (size_t)h->hb.total_s * esz;
-        size_t piece = total;
-        if (const char *e = getenv("TB2_H2D_PIECE_MB")) piece = (size_t)atoll(e) << 20;
-        else if (ctx->async_mode) piece = (size_t)16 << 20;
-        if (piece == 0) piece = total;
-        for (size_t off = 0; off < total; off += piece)
-            TB2_CUDA_TRY(ctx, cudaMemcpyAsync((char *)P[B_RAWIN].p + off, (const char *)raw + off,
-                                              std::min(piece, total - off), cudaMemcpyHostToDevice, s));
-    }
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[B_RAWIN].p, raw, (size_t)h->hb.total_s * esz, cudaMemcpyHostToDevice, s));
     if (ctx->ev_h1) cudaEventRecord(ctx->ev_h1, s);
     if (!ctx->async_mode) TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     h->uploaded = true;
@@ -379,7 +371,7 @@ extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, 
     return TB2_OK;
 }
 
-extern "C" int tb2_batch_set_read_inputs(tb2_ctx *ctx, const tb2_scale_values *sv_in,
+static int batch_set_read_inputs_impl(tb2_ctx *ctx, const tb2_scale_values *sv_in,
                                          const int64_t *stall_ints, const int64_t *stall_off)
 {
     int rc = tb2_use(ctx);
@@ -417,7 +409,7 @@ extern "C" int tb2_batch_set_read_inputs(tb2_ctx *ctx, const tb2_scale_values *s
     return TB2_OK;
 }
 
-extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
+static int batch_compute_impl(tb2_ctx *ctx, const tb2_params *params,
                                  const tb2_params *save_params, const tb2_policy *policy,
                                  int want_norm_signal)
 {
@@ -527,7 +519,7 @@ extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
     return TB2_OK;
 }
 
-extern "C" int tb2_batch_download(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_rel_to_raw,
+static int batch_download_impl(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_rel_to_raw,
                                   tb2_scale_values *scale_out, double *sig_match_score,
                                   double *norm_mean, double *norm_signal, int32_t *status,
                                   int32_t *n_iters, int32_t *flags)
@@ -566,7 +558,7 @@ extern "C" int tb2_batch_download(tb2_ctx *ctx, int64_t *segs, int64_t *read_sta
     return TB2_OK;
 }
 
-extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
+static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
                                     const int64_t *raw_off, const uint8_t *seq,
                                     const int64_t *seq_off, const tb2_params *params,
                                     const tb2_params *save_params, const tb2_policy *policy,
@@ -935,4 +927,58 @@ extern "C" int tb2_identify_stalls(tb2_ctx *ctx, const double *raw, int64_t n, i
     for (int i = 0; i < 2 * st.n_stalls; ++i) ints_out[i] = h[i];
     *n_out = st.n_stalls;
     return TB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI entry points of the batch path: no C++ exception may cross the boundary
+// ---------------------------------------------------------------------------
+#define TB2_GUARD(ctx, call)                                                        \
+    try {                                                                           \
+        return call;                                                                \
+    } catch (const std::exception &e) {                                             \
+        if (ctx) (ctx)->err = std::string("host exception: ") + e.what();           \
+        return TB2_ERR_UNEXPECTED;                                                  \
+    } catch (...) {                                                                 \
+        if (ctx) (ctx)->err = "host exception";                                     \
+        return TB2_ERR_UNEXPECTED;                                                  \
+    }
+
+extern "C" int tb2_batch_upload(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
+                                const int64_t *raw_off, const uint8_t *seq, const int64_t *seq_off,
+                                const tb2_params *params, const tb2_policy *policy)
+{
+    TB2_GUARD(ctx, batch_upload_impl(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy));
+}
+
+extern "C" int tb2_batch_set_read_inputs(tb2_ctx *ctx, const tb2_scale_values *sv_in,
+                                         const int64_t *stall_ints, const int64_t *stall_off)
+{
+    TB2_GUARD(ctx, batch_set_read_inputs_impl(ctx, sv_in, stall_ints, stall_off));
+}
+
+extern "C" int tb2_batch_compute(tb2_ctx *ctx, const tb2_params *params,
+                                 const tb2_params *save_params, const tb2_policy *policy,
+                                 int want_norm_signal)
+{
+    TB2_GUARD(ctx, batch_compute_impl(ctx, params, save_params, policy, want_norm_signal));
+}
+
+extern "C" int tb2_batch_download(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_rel_to_raw,
+                                  tb2_scale_values *scale_out, double *sig_match_score,
+                                  double *norm_mean, double *norm_signal, int32_t *status,
+                                  int32_t *n_iters, int32_t *flags)
+{
+    TB2_GUARD(ctx, batch_download_impl(ctx, segs, read_start_rel_to_raw, scale_out, sig_match_score, norm_mean, norm_signal, status, n_iters, flags));
+}
+
+extern "C" int tb2_resquiggle_batch(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
+                                    const int64_t *raw_off, const uint8_t *seq,
+                                    const int64_t *seq_off, const tb2_params *params,
+                                    const tb2_params *save_params, const tb2_policy *policy,
+                                    int64_t *segs, int64_t *read_start_rel_to_raw,
+                                    tb2_scale_values *scale_out, double *sig_match_score,
+                                    double *norm_mean, double *norm_signal, int32_t *status,
+                                    int32_t *n_iters, int32_t *flags)
+{
+    TB2_GUARD(ctx, resquiggle_batch_impl(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, save_params, policy, segs, read_start_rel_to_raw, scale_out, sig_match_score, norm_mean, norm_signal, status, n_iters, flags));
 }
