@@ -154,8 +154,19 @@ k_normalize(BatchView b, StagePolicy pol, int first_call)
     __syncthreads();
     const double thresh = given ? NAN : pol.outlier_thresh;
     if (!isnan(thresh)) {                                                             // :559-563
-        const double med = tb2_block_median([&](int i) { return norm[i]; }, n, sm);
-        const double mad = tb2_block_median([&](int i) { return fabs(norm[i] - med); }, n, sm);
+        double med, mad;
+        if ((n & 1) && !use_const) {
+            // odd n: shift is an element of raw and scale an element of |raw - shift|.
+            // x -> (x - shift) / scale is monotone (each rounding is), so the middle
+            // order statistic of norm is the image of shift: (shift - shift) / scale = +0;
+            // |norm - 0| = |x - shift| / scale is monotone in |x - shift|, so its middle
+            // order statistic is scale / scale = 1 -- the values np.median returns.
+            med = 0.0;
+            mad = 1.0;
+        } else {
+            med = tb2_block_median([&](int i) { return norm[i]; }, n, sm);
+            mad = tb2_block_median([&](int i) { return fabs(norm[i] - med); }, n, sm);
+        }
         lo = med - (mad * thresh);
         hi = med + (mad * thresh);
     } else if (given) { lo = s.sv.lower_lim; hi = s.sv.upper_lim; }                   // :565-566
