@@ -139,8 +139,16 @@ k_normalize(BatchView b, StagePolicy pol, int first_call)
     double shift, scale, lo = NAN, hi = NAN;
     const bool given = s.use_sv != 0;
     const bool use_const = first_call && !isnan(pol.const_scale);
+    double mid_a = 0.0, mid_b = 0.0;     // the middle order statistic(s) of raw
     if (!given) {
-        shift = tb2_block_median([&](int i) { return raw[i]; }, n, sm);              // :541/:545
+        auto f_raw = [&](int i) { return raw[i]; };
+        if (n & 1) {
+            tb2_block_select2(f_raw, PredAll(), n, n / 2, false, &mid_a, &mid_b, sm);
+            shift = mid_a;                                                            // :541/:545
+        } else {
+            tb2_block_select2(f_raw, PredAll(), n, n / 2 - 1, true, &mid_a, &mid_b, sm);
+            shift = (mid_a + mid_b) / 2.0;
+        }
         if (use_const) scale = pol.const_scale;                                       // :546
         else scale = tb2_block_median([&](int i) { return fabs(raw[i] - shift); }, n, sm);  // :542
     } else {
@@ -164,7 +172,9 @@ k_normalize(BatchView b, StagePolicy pol, int first_call)
             med = 0.0;
             mad = 1.0;
         } else {
-            med = tb2_block_median([&](int i) { return norm[i]; }, n, sm);
+            // even n: the two middle elements of norm are the images of raw's
+            if (n & 1) med = tb2_block_median([&](int i) { return norm[i]; }, n, sm);
+            else med = (((mid_a - shift) / scale) + ((mid_b - shift) / scale)) / 2.0;
             mad = tb2_block_median([&](int i) { return fabs(norm[i] - med); }, n, sm);
         }
         lo = med - (mad * thresh);
