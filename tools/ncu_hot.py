@@ -1,5 +1,5 @@
 """helper (not a test): summarise an ncu --import-source capture: hot SASS runs by
-executed instructions.  usage: python tests/ncu_hot.py rep.ncu-rep [min_frac]"""
+executed instructions.  usage: python tools/ncu_hot.py rep.ncu-rep [min_frac]"""
 import csv, subprocess, sys, io
 
 

@@ -1,6 +1,6 @@
 """helper (not a test): attribute an ncu --import-source capture to CUDA source lines
 by joining its SASS rows (in address order) with nvdisasm -g line markers of the
-current build.  usage: python tests/ncu_lines.py rep.ncu-rep cubin mangled_kernel_name [top]"""
+current build.  usage: python tools/ncu_lines.py rep.ncu-rep cubin mangled_kernel_name [top]"""
 import csv, io, re, subprocess, sys, collections
 
 
