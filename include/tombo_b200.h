@@ -253,6 +253,11 @@ int tb2_resquiggle_batch(
     tb2_scale_values *scale_out, double *sig_match_score, double *norm_mean,
     double *norm_signal, int32_t *status, int32_t *n_iters, int32_t *flags);
 
+/* Host-only helper: the chunk schedule tb2_resquiggle_batch uses for n_reads on a device
+ * with sm_count SMs (chunk k = reads [starts_out[k], starts_out[k+1])).  Returns the
+ * number of chunks (1 = unpipelined) or a negated TB2_ERR_* code; needs no device. */
+int tb2_pipeline_chunks(int sm_count, int64_t n_reads, int64_t *starts_out, int cap);
+
 /* The same call in three stages, for callers that keep inputs resident in HBM or
  * overlap transfers themselves: upload (H2D of raw / seq, allocation), compute
  * (kernels only, results stay on the device), download (D2H into caller buffers

@@ -83,3 +83,31 @@ def test_parameters_and_namedtuples_match_reference_when_available():
                                                    use_save_bandwidth=save)
             assert tuple(a) == tuple(b)
     assert ts.HALF_NORM_EXPECTED_VAL == m['ts'].HALF_NORM_EXPECTED_VAL
+
+
+def test_pipeline_chunk_schedule_covers_every_read_once():
+    """host-only part of tb2_resquiggle_batch: the chunk schedule (no device needed)"""
+    import numpy as np
+    from tombo_b200 import _lib
+    lib = _lib.load()
+    fn = lib.tb2_pipeline_chunks
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+    buf = (ctypes.c_int64 * 4096)()
+    sm = 148
+    unit = sm * 32
+    for n in [0, 1, unit, 6 * unit, 6 * unit + 1, 39122, 100000, 1000003]:
+        k = fn(sm, n, buf, 4096)
+        assert k >= 1, (n, k)
+        starts = np.array(buf[:k + 1])
+        assert starts[0] == 0 and starts[-1] == n
+        sizes = np.diff(starts)
+        if n > 0:
+            assert np.all(sizes > 0)
+        assert np.all(sizes <= 8 * unit) or k == 1
+        if n <= 6 * unit:
+            assert k == 1                     # small batches are not pipelined
+        else:
+            assert k >= 2 and sizes[0] == 2 * unit   # short first chunk: its upload is exposed
+    assert fn(sm, 10 ** 9, buf, 8) < 0        # capacity is reported, not overrun
+    assert fn(sm, -1, buf, 8) < 0

@@ -558,6 +558,39 @@ static int batch_download_impl(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_
     return TB2_OK;
 }
 
+// Chunk schedule of the pipelined batch call (host only).  U = one read per resident DP
+// warp of the lean kernel.  Up to 6 U reads go as one batch (returns 1 chunk); larger
+// batches start with short chunks (the first upload is the only exposed one), continue
+// with chunks of 8 U (few launches, short tails) and end with the remainder.
+static std::vector<int64_t> pipeline_chunk_starts(int sm_count, int64_t n_reads)
+{
+    std::vector<int64_t> cs;
+    const int64_t U = (int64_t)std::max(1, sm_count) * 32, CH = 8 * U;
+    int64_t at = 0;
+    if (n_reads > 6 * U) {
+        const int64_t ramp[2] = {2 * U, 4 * U};
+        for (int q = 0; q < 2 && n_reads - at > ramp[q]; ++q) { cs.push_back(at); at += ramp[q]; }
+        while (at < n_reads) { cs.push_back(at); at += CH; }
+    } else {
+        cs.push_back(0);
+    }
+    cs.push_back(n_reads);
+    return cs;
+}
+
+extern "C" int tb2_pipeline_chunks(int sm_count, int64_t n_reads, int64_t *starts_out, int cap)
+{
+    if (n_reads < 0 || !starts_out || cap < 2) return -TB2_ERR_INVALID_ARG;
+    try {
+        const std::vector<int64_t> cs = pipeline_chunk_starts(sm_count, n_reads);
+        if ((int)cs.size() > cap) return -TB2_ERR_CAPACITY;
+        for (size_t i = 0; i < cs.size(); ++i) starts_out[i] = cs[i];
+        return (int)cs.size() - 1;
+    } catch (...) {
+        return -TB2_ERR_UNEXPECTED;
+    }
+}
+
 static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
                                     const int64_t *raw_off, const uint8_t *seq,
                                     const int64_t *seq_off, const tb2_params *params,
@@ -574,10 +607,8 @@ static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw,
         !read_start_rel_to_raw || !scale_out || !sig_match_score || !status || !n_iters || !flags ||
         (raw_dtype != 0 && raw_dtype != 1) || n_reads > 0x7ffffff0)
         return TB2_ERR_INVALID_ARG;
-    // chunk sizes in units of one read per resident DP warp of the lean kernel
-    const int64_t U = (int64_t)ctx->sm_count * 32;
-    const int64_t CH = 8 * U;
-    if (n_reads <= 6 * U) {
+    const std::vector<int64_t> cstart = pipeline_chunk_starts(ctx->sm_count, n_reads);
+    if (cstart.size() <= 2) {
         rc = tb2_batch_upload(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy);
         if (rc) return rc;
         if ((rc = tb2_batch_compute(ctx, params, save_params, policy, norm_signal != nullptr))) return rc;
@@ -607,24 +638,13 @@ static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw,
     }
     const int K = ctx->kmer_width;
     const int n = (int)n_reads;
-    // chunk starts: short first chunks (the first upload is the only exposed one), then
-    // chunks of 8 reads per resident DP warp (few launches, short tails), the remainder
-    // last
-    std::vector<int> cstart;
-    {
-        int64_t at = 0;
-        const int64_t ramp[2] = {2 * U, 4 * U};
-        for (int q = 0; q < 2 && n_reads - at > ramp[q]; ++q) { cstart.push_back((int)at); at += ramp[q]; }
-        while (at < n_reads) { cstart.push_back((int)at); at += CH; }
-        cstart.push_back((int)n_reads);
-    }
     const int n_chunks = (int)cstart.size() - 1;
     std::vector<int64_t> base_off((size_t)n + 1, 0);
     for (int r = 0; r < n; ++r)
         base_off[r + 1] = base_off[r] + std::max<int64_t>(0, (seq_off[r + 1] - seq_off[r]) - (K - 1));
     std::vector<std::vector<int64_t>> ro((size_t)n_chunks), so((size_t)n_chunks);
     const size_t esz = raw_dtype == 0 ? 8 : 2;
-    auto bounds = [&](int k, int *a, int *b) { *a = cstart[k]; *b = cstart[k + 1]; };
+    auto bounds = [&](int k, int *a, int *b) { *a = (int)cstart[k]; *b = (int)cstart[k + 1]; };
     auto upload = [&](int k) -> int {
         int a, b;
         bounds(k, &a, &b);
