@@ -159,3 +159,84 @@ def test_fp32_screen_never_contradicts_the_fp64_slope():
                 assert np.all(s[high] >= T)
                 checked += int(low.sum() + high.sum())
     assert checked > 100000
+
+
+# ---------------------------------------------------------------------------
+# wavefront engine: the predicated ("lean") cell update == the reference row update
+# (c_banded_forward_pass inner loop, _c_dynamic_programming.pyx:213-234)
+# ---------------------------------------------------------------------------
+def _row_reference(prev, z, d, stay, skip):
+    W = prev.shape[0]
+    NEG = -np.inf
+    out = np.empty(W)
+    codes = np.empty(W, dtype=np.int64)
+    x = 0.0
+    for j in range(W):
+        p = j + d
+        u = prev[p] if p < W else NEG
+        ul = prev[p - 1] if 1 <= p <= W else NEG
+        if j == 0:
+            if d == 0:
+                nx, code = u - skip, 1            # band did not move: skip, no stay / diag
+            else:
+                nx, code = ul + z[j], 2           # band moved: diagonal only
+        else:
+            a = (x - stay) + z[j]
+            cc, cf = ul + z[j], 2
+            sk = u - skip
+            if sk > cc:
+                cc, cf = sk, 1
+            if cc > a:
+                nx, code = cc, cf
+            else:
+                nx, code = a, 0
+        out[j], codes[j] = nx, code
+        x = nx
+    return out, codes
+
+
+def _row_lean(prev, z, d, stay, skip):
+    """one formula for every cell: x starts at -inf, the cells above / above-left are
+    replaced by -inf outside their validity ranges (dp_row.cuh TB2_WF_LEAN_STEP)"""
+    W = prev.shape[0]
+    NEG = -np.inf
+    julo = 1 if d >= 1 else 0
+    jllo = 1 - julo
+    n_u = max(W - d - julo, 0)
+    n_ul = max(W - d - jllo + 1, 0)
+    out = np.empty(W)
+    codes = np.empty(W, dtype=np.int64)
+    x = NEG
+    for j in range(W):
+        p = j + d
+        u = prev[p] if 0 <= j - julo < n_u else NEG
+        ul = prev[p - 1] if 0 <= j - jllo < n_ul else NEG
+        a = (x - stay) + z[j]
+        cc, code = ul + z[j], 2
+        sk = u - skip
+        if sk > cc:
+            cc, code = sk, 1
+        nx = a
+        if cc > a:
+            nx = cc
+        else:
+            code = 0
+        out[j], codes[j] = nx, code
+        x = nx
+    return out, codes
+
+
+def test_lean_wavefront_step_equals_reference_row_update():
+    rs = np.random.RandomState(21)
+    for trial in range(400):
+        W = rs.randint(2, 40)
+        d = rs.randint(0, min(6, W))
+        prev = 5.0 * rs.standard_normal(W)
+        z = 3.0 - np.abs(2.0 * rs.standard_normal(W))
+        if trial % 5 == 0:
+            z = np.round(z)                       # exact ties between the three moves
+            prev = np.round(prev)
+        a, ca = _row_reference(prev, z, d, 4.0, 4.0)
+        b, cb = _row_lean(prev, z, d, 4.0, 4.0)
+        assert np.array_equal(a, b), (trial, W, d)
+        assert np.array_equal(ca, cb), (trial, W, d)
