@@ -185,3 +185,26 @@ def test_identify_stalls_matches_oracle(orc):
     exp = orc.identify_stalls(raw)
     assert len(exp) >= 1
     assert np.array_equal(np.array(got).reshape(-1, 2), exp)
+
+
+def test_read_batcher_streams_the_golden_reads_in_order():
+    """tombo_b200.worker over the real backend: small batches, results in
+    submission order, failures as the reference's wire messages"""
+    from tombo_b200 import worker
+    g = gu.load('dna_rescue')
+    kind, kmer_ref, cpos, reads = gu.reads_of(g)
+    aln = tuple(float(a) if i in (0, 1, 4) else int(a) for i, a in enumerate(tuple(g['aln'])))
+    th, ts, syn, _, _, std_ref, sst, p, sp = _setup(kind, aln)
+    stream = ((_map_res(th, r.raw, r.genome_seq), 'read%d.fast5' % i) for i, r in enumerate(reads))
+    fs = worker.FailureSummary()
+    out = list(worker.resquiggle_stream(stream, std_ref, p, sp, max_reads=3,
+                                        outlier_thresh=5.0, seq_samp_type=sst))
+    assert [fn for fn, _ in out] == ['read%d.fast5' % i for i in range(len(reads))]
+    for i, (fn, msg) in enumerate(out):
+        fs.record(msg)
+        e = gu.expected(g, i)
+        if e['message']:
+            assert msg == [True, [e['message'], fn, True]]
+        else:
+            assert msg[0] is False and np.array_equal(msg[1].segs, e['segs'])
+    assert fs.num_processed == len(reads)
