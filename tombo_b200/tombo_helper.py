@@ -215,3 +215,108 @@ def get_multiple_slots_read_centric(r_data, slot_names, corr_grp=None):
         return [events[name] for name in slot_names]
     except Exception:
         return [None] * len(slot_names)
+
+
+# ---- FAST5 Events table: the output seam of the resquiggle path ----
+EVENTS_DTYPE = [(str('norm_mean'), 'f8'), (str('norm_stdev'), 'f8'), (str('start'), 'u4'),
+                (str('length'), 'u4'), (str('base'), 'S1')]   # tombo_helper.py:2361-2364
+
+
+def events_table(rsqgl_res, compute_sd=False, norm_means=None, norm_stds=None, device=0):
+    """The per-base ``Events`` table the reference stores (tombo_helper.py:2347-2364):
+    norm_mean, norm_stdev (NaN unless ``compute_sd``), start, length, base.  The means
+    (and standard deviations) are the device's c_new_means / c_new_mean_stds unless the
+    caller already holds them (``tb2_resquiggle_batch`` returns ``norm_mean``)."""
+    segs = np.asarray(rsqgl_res.segs, dtype=np.int64)
+    n = segs.shape[0] - 1
+    if norm_means is None or (compute_sd and norm_stds is None):
+        ctx = _lib.get_context(device)
+        if compute_sd:
+            norm_means, norm_stds = ctx.new_mean_stds(rsqgl_res.raw_signal, segs)
+        else:
+            norm_means = ctx.new_means(rsqgl_res.raw_signal, segs)
+    if len(rsqgl_res.genome_seq) != n or len(norm_means) != n:
+        raise TomboError('Error computing new events')
+    ev = np.empty(n, dtype=EVENTS_DTYPE)
+    ev['norm_mean'] = norm_means
+    ev['norm_stdev'] = norm_stds if compute_sd else np.nan
+    ev['start'] = segs[:-1]
+    ev['length'] = np.diff(segs)
+    ev['base'] = np.frombuffer(rsqgl_res.genome_seq.encode('ascii'), dtype='S1')
+    return ev
+
+
+def new_fast5_group_layout(rsqgl_res, norm_type, event_data, rna=False, alignVals=None,
+                           old_segs=None):
+    """What write_new_fast5_group stores under ``/Analyses/<corr_grp>/<subgroup>``
+    (tombo_helper.py:2386-2443) as plain data: ``(attrs, alignment_attrs, datasets,
+    events_attrs)``; ``datasets`` maps 'Alignment/<name>' / 'Events' to arrays."""
+    sv = rsqgl_res.scale_values
+    attrs = [('status', 'success'), ('rna', rna)]
+    if rsqgl_res.sig_match_score is not None:
+        attrs.append(('signal_match_score', rsqgl_res.sig_match_score))
+    attrs += [('shift', sv.shift), ('scale', sv.scale), ('norm_type', norm_type)]
+    for name, val in (('lower_lim', sv.lower_lim), ('upper_lim', sv.upper_lim),
+                      ('outlier_threshold', sv.outlier_thresh)):
+        if val is not None:
+            attrs.append((name, val))
+    gl = rsqgl_res.genome_loc
+    aln = [('mapped_start', gl.Start), ('mapped_end', gl.Start + len(rsqgl_res.segs) - 1),
+           ('mapped_strand', gl.Strand), ('mapped_chrom', gl.Chrom)]
+    ai = rsqgl_res.align_info
+    if ai is not None:
+        aln += [('clipped_bases_start', ai.ClipStart), ('clipped_bases_end', ai.ClipEnd),
+                ('num_insertions', ai.Insertions), ('num_deletions', ai.Deletions),
+                ('num_matches', ai.Matches), ('num_mismatches', ai.Mismatches)]
+    datasets = []
+    if alignVals is not None:
+        r_vals, g_vals = zip(*alignVals)
+        datasets.append(('Alignment/read_alignment', np.array(r_vals, dtype='S1')))
+        datasets.append(('Alignment/genome_alignment', np.array(g_vals, dtype='S1')))
+    if old_segs is not None:
+        datasets.append(('Alignment/read_segments', np.asarray(old_segs)))
+    datasets.append(('Events', event_data))
+    return attrs, aln, datasets, [('read_start_rel_to_raw', rsqgl_res.read_start_rel_to_raw)]
+
+
+def write_new_fast5_group(fast5_data, corr_grp_slot, rsqgl_res, norm_type, compute_sd,
+                          alignVals=None, old_segs=None, rna=False, norm_means=None,
+                          norm_stds=None):
+    """tombo_helper.py:2341-2460 over any h5py-like object (``fast5_data`` may be an open
+    ``h5py.File`` or a path; h5py itself is outside this package's requirements)."""
+    event_data = events_table(rsqgl_res, compute_sd, norm_means, norm_stds)
+    attrs, aln, datasets, ev_attrs = new_fast5_group_layout(
+        rsqgl_res, norm_type, event_data, rna, alignVals, old_segs)
+    do_close = False
+    if isinstance(fast5_data, str):
+        try:
+            import h5py
+            fast5_data = h5py.File(fast5_data, 'r+')
+            do_close = True
+        except Exception:
+            raise TomboError('Error opening file for new group writing. This should have '
+                             'been caught during the alignment phase. Check that there are '
+                             'no other tombo processes or processes accessing these HDF5 '
+                             'files running simultaneously.')
+    try:
+        corr_subgrp = fast5_data['/Analyses'][corr_grp_slot].create_group(
+            rsqgl_res.align_info.Subgroup)
+        for k, v in attrs:
+            corr_subgrp.attrs[k] = v
+        corr_alignment = corr_subgrp.create_group('Alignment')
+        for k, v in aln:
+            corr_alignment.attrs[k] = v
+        for name, data in datasets:
+            if name == 'Events':
+                ds = corr_subgrp.create_dataset('Events', data=data, compression='gzip')
+                for k, v in ev_attrs:
+                    ds.attrs[k] = v
+            else:
+                corr_alignment.create_dataset(name.split('/', 1)[1], data=data, compression='gzip')
+    except Exception:
+        raise TomboError('Error writing resquiggle information back into fast5 file.')
+    if do_close:
+        try:
+            fast5_data.close()
+        except Exception:
+            raise TomboError('Error closing fast5 file after writing resquiggle information.')
