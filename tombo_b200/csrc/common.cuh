@@ -5,7 +5,9 @@
 // reference's operation order and WITHOUT fused multiply-add (compile with
 // -fmad=false); the reference's Cython objects contain no FMA.
 #pragma once
+#ifndef TB2_EMUL   // tests/emul/cuda_emul.h stands in for the CUDA headers on the host
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <math.h>
 #include "../../include/tombo_b200.h"

@@ -160,6 +160,10 @@ __device__ __forceinline__ int tb2_warp_argmax(double best, int best_idx)
 // re-walked, [3] rows that needed more than 2 rounds
 __device__ unsigned long long g_tb2_dp_counters[8];
 
+#ifdef TB2_EMUL
+__device__ __forceinline__ double tb2_lds(unsigned a) { return *(double *)emul_shared_ptr(a); }
+__device__ __forceinline__ void tb2_sts(unsigned a, double v) { *(double *)emul_shared_ptr(a) = v; }
+#else
 __device__ __forceinline__ double tb2_lds(unsigned a)
 {
     double v;
@@ -170,6 +174,7 @@ __device__ __forceinline__ void tb2_sts(unsigned a, double v)
 {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v));
 }
+#endif
 
 // prev_s / cur_s / z_s / c_s: shared-memory byte addresses of four lane-transposed
 // row buffers (previous row, current row, z-scores, best diag/skip candidate)
@@ -539,28 +544,34 @@ __device__ __forceinline__ double tb2_wf_z(const double *ep, int j, double mu, d
 template <bool RBS>
 __device__ __forceinline__ double tb2_rb_ld(const double *rb, unsigned rb_s, int i)
 {
-    if (RBS) {
-        double v;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(rb_s + 8u * (unsigned)i));
-        return v;
-    }
+    if (RBS) return tb2_lds(rb_s + 8u * (unsigned)i);
     return rb[i];
 }
 template <bool RBS>
 __device__ __forceinline__ void tb2_rb_st(double *rb, unsigned rb_s, int i, double v)
 {
-    if (RBS) asm volatile("st.shared.f64 [%0], %1;" ::"r"(rb_s + 8u * (unsigned)i), "d"(v));
+    if (RBS) tb2_sts(rb_s + 8u * (unsigned)i, v);
     else rb[i] = v;
 }
 
 // one steady-state step (U = position inside the 16-step group): lane 0 takes the
 // cell above from the row buffer (predicated load at a running address), the tail
 // lane stores its result there; moves enter the word by a funnel shift.
+#ifdef TB2_EMUL
+#define TB2_WF_PLD(up, U) if (l0flag) up = tb2_lds(rd_a + 8 * (U));
+#define TB2_WF_PST(nx, U) if (tlflag) tb2_sts(wr_a + 8 * (U), nx);
+#else
+#define TB2_WF_PLD(up, U)                                                                       \
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.f64 %0, [%1+%3]; }"    \
+                     : "+d"(up) : "r"(rd_a), "r"(l0flag), "n"(8 * (U)));
+#define TB2_WF_PST(nx, U)                                                                       \
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0+%3], %1; }"    \
+                     :: "r"(wr_a), "d"(nx), "r"(tlflag), "n"(8 * (U)) : "memory");
+#endif
 #define TB2_WF_FAST_STEP(U)                                                                     \
     {                                                                                           \
         double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);                                     \
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.f64 %0, [%1+%3]; }"    \
-                     : "+d"(up) : "r"(rd_a), "r"(l0flag), "n"(8 * (U)));                        \
+        TB2_WF_PLD(up, U)                                                                       \
         const double zn = tb2_wf_z<MODE, WIN>(ep + (U) + 1, j + (U) + 1, mu, sd, inv_sd, lo,    \
                                               hi, maskval, nullptr, zs, mhz);                   \
         const double a = (x - stay) + z;                                                        \
@@ -573,8 +584,7 @@ __device__ __forceinline__ void tb2_rb_st(double *rb, unsigned rb_s, int i, doub
         up_prev = up;                                                                           \
         x = nx; xout = nx; z = zn;                                                              \
         cw = __funnelshift_r(cw, code, 2);                                                      \
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0+%3], %1; }"    \
-                     :: "r"(wr_a), "d"(nx), "r"(tlflag), "n"(8 * (U)) : "memory");              \
+        TB2_WF_PST(nx, U)                                                                       \
     }
 
 template <int MODE, bool DBG, bool WIN, bool RBS>

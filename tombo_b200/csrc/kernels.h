@@ -1,6 +1,12 @@
 // kernels.h -- internal launch interfaces between translation units
 #pragma once
+#ifdef TB2_EMUL   // host emulation of the device code (tests/emul): no CUDA runtime types
+#include <stddef.h>
+#include "../../include/tombo_b200.h"
+struct tb2_ctx;
+#else
 #include "ctx.h"
+#endif
 
 // Device-resident batch description for the event->sequence assignment kernel.
 // All arrays live in device memory.  Read r owns
