@@ -57,6 +57,8 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
                const tb2_params &p, double ratio, int is_rna, HostBatch &hb, BatchView &v)
 {
     hb.n = n;
+    long long max_raw_pre = 0;
+    for (int r = 0; r < n; ++r) max_raw_pre = std::max<long long>(max_raw_pre, raw_off[r + 1] - raw_off[r]);
     hb.base_off.assign(n + 1, 0);
     hb.ev_off.assign(n + 1, 0);
     for (int r = 0; r < n; ++r) {
@@ -68,8 +70,7 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
         hb.base_off[r + 1] = hb.base_off[r] + nb;
         hb.ev_off[r + 1] = hb.ev_off[r] + std::max<long long>(2, num_events_of(s, nb, p, ratio)) + 1;
     }
-    long long max_raw = 0;
-    for (int r = 0; r < n; ++r) max_raw = std::max<long long>(max_raw, raw_off[r + 1] - raw_off[r]);
+    const long long max_raw = max_raw_pre;
     v.max_raw = (int)max_raw;
     hb.total_s = raw_off[n] - raw_off[0];
     hb.total_seq = seq_off[n] - seq_off[0];
@@ -78,7 +79,9 @@ int build_view(tb2_ctx *ctx, int n, const int64_t *raw_off, const int64_t *seq_o
     if (raw_off[0] != 0 || seq_off[0] != 0) return TB2_ERR_INVALID_ARG;
     auto &P = ctx->pool;
     const size_t S = (size_t)hb.total_s, Bn = (size_t)hb.total_b, E = (size_t)hb.total_e;
-    const int stall_cap = 64;
+    // a stall needs > 200 consecutive observations (MEAN_STALL_PARAMS), so a read of S
+    // samples holds at most S / 200 + 1 intervals: size the slots from the longest read
+    const int stall_cap = (int)std::max<long long>(8, max_raw_pre / 200 + 4);
     TB2_CUDA_TRY(ctx, P[B_RAWOFF].reserve((n + 1) * 8));
     TB2_CUDA_TRY(ctx, P[B_SEQOFF].reserve((n + 1) * 8));
     TB2_CUDA_TRY(ctx, P[B_BASEOFF].reserve((n + 1) * 8));

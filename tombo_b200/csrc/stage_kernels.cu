@@ -496,6 +496,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_rna_scale(BatchView b, StagePoli
     const int r = blockIdx.x;
     ReadState &s = b.st[r];
     if (!rd_active(s) || s.use_sv == 1) return;
+    // a caller-supplied const_scale wins over the event-based scaling: segment_signal
+    // takes the 'median_const_scale' branch (resquiggle.py:1084-1087), k_normalize does it
+    if (!isnan(pol.const_scale)) return;
     const double *raw = b.rawf + b.raw_off[r];
     const int *cp = b.cpts + b.ev_off[r];
     double *em = b.em + b.ev_off[r];

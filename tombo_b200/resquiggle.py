@@ -34,10 +34,14 @@ def _seq_codes(seq):
 
 
 def _ensure_model(ctx, std_ref):
-    if getattr(ctx, '_model_id', None) != id(std_ref):
-        m, s = std_ref.tables()
+    """upload the k-mer tables once per model object.  The context keeps a strong
+    reference (an id() alone can be recycled after garbage collection) and a digest of
+    the tables, so a model mutated in place is uploaded again."""
+    m, s = std_ref.tables()
+    digest = hash((m.tobytes(), s.tobytes(), std_ref.kmer_width, std_ref.central_pos))
+    if getattr(ctx, '_model_ref', None) is not std_ref or getattr(ctx, '_model_digest', None) != digest:
         ctx.set_model(m, s, std_ref.kmer_width, std_ref.central_pos)
-        ctx._model_id = id(std_ref)
+        ctx._model_ref, ctx._model_digest = std_ref, digest
 
 
 # ---------------------------------------------------------------------------
@@ -97,93 +101,116 @@ def resolve_skipped_bases_with_raw(
 
 
 def _remove_stall_cpts(stall_ints, valid_cpts):
-    # tombo_stats.py:1576-1597 (pure Python in the reference as well)
-    if len(stall_ints) == 0:
+    """Drop changepoints strictly inside a stall interval (tombo_stats.py:1576-1597).
+    The reference walks the sorted intervals next to the sorted changepoints; with sorted,
+    disjoint intervals that is an interval lookup: the only interval that can hold cpt is
+    the first one whose end is >= cpt."""
+    stall_ints = np.asarray(stall_ints, dtype=np.int64).reshape(-1, 2)
+    if stall_ints.shape[0] == 0:
         return valid_cpts
-    it = iter(stall_ints)
-    cur = next(it)
-    keep = []
-    for i, cpt in enumerate(valid_cpts):
-        while cpt > cur[1]:
-            try:
-                cur = next(it)
-            except StopIteration:
-                break
-        if not (cur[0] < cpt < cur[1]):
-            keep.append(i)
-    return valid_cpts[keep]
+    k = np.searchsorted(stall_ints[:, 1], valid_cpts, side='left')
+    kc = np.minimum(k, stall_ints.shape[0] - 1)
+    inside = (k < stall_ints.shape[0]) & (stall_ints[kc, 0] < valid_cpts) & \
+        (valid_cpts < stall_ints[kc, 1])
+    return valid_cpts[~inside]
+
+
+def _rna_event_scale_values(raw, valid_cpts, outlier_thresh):
+    """get_scale_values_from_events (tombo_stats.py:217-233): median / MAD of the first
+    RNA_SCALE_NUM_EVENTS (at most RNA_SCALE_MAX_FRAC_EVENTS of all) event means."""
+    n_ev = RNA_SCALE_NUM_EVENTS
+    if valid_cpts.shape[0] * RNA_SCALE_MAX_FRAC_EVENTS < n_ev:
+        n_ev = int(valid_cpts.shape[0] * RNA_SCALE_MAX_FRAC_EVENTS)
+    ev_means = ts.compute_base_means(raw, valid_cpts[:n_ev])
+    _, ev_sv = ts.normalize_raw_signal(ev_means, norm_type='median')
+    return th.scaleValues(ev_sv.shift, ev_sv.scale, -outlier_thresh, outlier_thresh, None)
 
 
 def segment_signal(map_res, num_events, rsqgl_params, outlier_thresh=None, const_scale=None):
-    """resquiggle.py:1057-1120 -> (valid_cpts, norm_signal, scale_values)"""
+    """resquiggle.py:1057-1120 -> (valid_cpts, norm_signal, scale_values).
+
+    Two orders of the same two steps: RNA (t-test segmentation) finds changepoints on the
+    raw signal and may derive the scaling from the events; DNA normalises first and
+    segments the normalised signal.  Which normalisation runs is one precedence list:
+    scale values carried by the read > ``const_scale`` > estimated from the signal."""
     raw = map_res.raw_signal
-    if rsqgl_params.use_t_test_seg:
-        valid_cpts = th.valid_cpts_w_cap_t_test(
-            raw.astype(np.float64), rsqgl_params.min_obs_per_base,
-            rsqgl_params.running_stat_width, num_events)
-        if map_res.stall_ints is not None:
-            valid_cpts = _remove_stall_cpts(map_res.stall_ints, valid_cpts)
+    rna = bool(rsqgl_params.use_t_test_seg)
+
+    def changepoints(sig):
+        find = th.valid_cpts_w_cap_t_test if rna else th.valid_cpts_w_cap
+        cpts = find(sig.astype(np.float64) if rna else sig, rsqgl_params.min_obs_per_base,
+                    rsqgl_params.running_stat_width, num_events)
+        return cpts if map_res.stall_ints is None else _remove_stall_cpts(map_res.stall_ints, cpts)
+
+    def normalise(event_cpts):
         if map_res.scale_values is not None:
-            norm_signal, new_sv = ts.normalize_raw_signal(raw, scale_values=map_res.scale_values)
-        elif const_scale is not None:
-            norm_signal, new_sv = ts.normalize_raw_signal(
-                raw, norm_type='median_const_scale', outlier_thresh=outlier_thresh,
-                const_scale=const_scale)
-        else:
-            scale_values = None
-            if USE_RNA_EVENT_SCALE:
-                # get_scale_values_from_events tombo_stats.py:217-233: median / MAD of
-                # the event means, both from the normalisation kernel
-                cp = valid_cpts
-                ne = RNA_SCALE_NUM_EVENTS
-                if cp.shape[0] * RNA_SCALE_MAX_FRAC_EVENTS < ne:
-                    ne = int(cp.shape[0] * RNA_SCALE_MAX_FRAC_EVENTS)
-                ev = ts.compute_base_means(raw, cp[:ne])
-                _, ev_sv = ts.normalize_raw_signal(ev, norm_type='median')
-                scale_values = th.scaleValues(ev_sv.shift, ev_sv.scale, -outlier_thresh,
-                                              outlier_thresh, None)
-            norm_signal, new_sv = ts.normalize_raw_signal(raw, scale_values=scale_values)
+            return ts.normalize_raw_signal(raw, scale_values=map_res.scale_values)
+        if const_scale is not None:
+            return ts.normalize_raw_signal(raw, norm_type='median_const_scale',
+                                           outlier_thresh=outlier_thresh, const_scale=const_scale)
+        if not rna:
+            return ts.normalize_raw_signal(raw, norm_type='median', outlier_thresh=outlier_thresh)
+        sv = _rna_event_scale_values(raw, event_cpts, outlier_thresh) if USE_RNA_EVENT_SCALE else None
+        return ts.normalize_raw_signal(raw, scale_values=sv)
+
+    if rna:
+        valid_cpts = changepoints(raw)
+        norm_signal, new_sv = normalise(valid_cpts)
     else:
-        if map_res.scale_values is not None:
-            norm_signal, new_sv = ts.normalize_raw_signal(raw, scale_values=map_res.scale_values)
-        elif const_scale is not None:
-            norm_signal, new_sv = ts.normalize_raw_signal(
-                raw, norm_type='median_const_scale', outlier_thresh=outlier_thresh,
-                const_scale=const_scale)
-        else:
-            norm_signal, new_sv = ts.normalize_raw_signal(
-                raw, norm_type='median', outlier_thresh=outlier_thresh)
-        valid_cpts = th.valid_cpts_w_cap(
-            norm_signal, rsqgl_params.min_obs_per_base, rsqgl_params.running_stat_width,
-            num_events)
-        if map_res.stall_ints is not None:
-            valid_cpts = _remove_stall_cpts(map_res.stall_ints, valid_cpts)
+        norm_signal, new_sv = normalise(None)
+        valid_cpts = changepoints(norm_signal)
     return valid_cpts, norm_signal, new_sv
 
 
 # ---------------------------------------------------------------------------
 # batched driver shared by resquiggle_read / resquiggle_reads
 # ---------------------------------------------------------------------------
-def _run_batch(map_results, std_ref, rsqgl_params, save_params, outlier_thresh, max_raw_cpts,
-               min_event_to_seq_ratio, const_scale, skip_seq_scaling, seq_samp_type,
-               max_scaling_iters, worker_policy, subsample_seed, device):
-    ctx = _lib.get_context(device)
-    _ensure_model(ctx, std_ref)
+def pack_reads(map_results):
+    """Flat batch arrays of the C ABI (raw, raw_off, seq codes, seq_off); host only.
+
+    A read whose ``raw_signal`` is None contributes an empty slice: the library reports
+    TB2_ERR_NO_RAW for exactly that read ('Must have raw signal ...', resquiggle.py:1149)
+    and the rest of the batch is unaffected, as in the reference where only that read's
+    resquiggle_read raises."""
     n = len(map_results)
-    raws = []
-    for mr in map_results:
-        if mr.raw_signal is None:
-            raise th.TomboError(
-                'Must have raw signal in order to complete re-squiggle algorithm')
-        raws.append(np.asarray(mr.raw_signal))
+    raws = [np.zeros(0, dtype=np.int16) if mr.raw_signal is None else np.asarray(mr.raw_signal)
+            for mr in map_results]
     all_int16 = all(r.dtype == np.int16 for r in raws)
-    raw = np.concatenate([r if all_int16 else r.astype(np.float64) for r in raws])
+    raw = np.concatenate([r if all_int16 else r.astype(np.float64) for r in raws]) if n else \
+        np.zeros(0, dtype=np.float64)
+    if raw.shape[0] == 0:
+        raw = np.zeros(1, dtype=raw.dtype)     # the library wants a non-null buffer
     raw_off = np.zeros(n + 1, dtype=np.int64)
     raw_off[1:] = np.cumsum([r.shape[0] for r in raws])
     codes = [_seq_codes(mr.genome_seq) for mr in map_results]
     seq = np.concatenate(codes)
     seq_off = np.zeros(n + 1, dtype=np.int64)
     seq_off[1:] = np.cumsum([c.shape[0] for c in codes])
+    return raw, raw_off, seq, seq_off
+
+
+class LibraryError(Exception):
+    """A per-read outcome that is NOT a TomboError in the reference: the reference's
+    'Unexpected error' bucket (FloatingPointError etc., resquiggle.py:1589-1594) and this
+    library's own limits (CUDA failure, compiled-in capacity).  The worker files these
+    with is_tombo_error=False."""
+
+
+_NON_TOMBO_STATUS = (100, 200, 201, 202)   # UNEXPECTED, CUDA, INVALID_ARG, CAPACITY
+
+
+def _status_exception(st):
+    msg = _lib.status_message(st)
+    return LibraryError(msg) if st in _NON_TOMBO_STATUS else th.TomboError(msg)
+
+
+def _run_batch(map_results, std_ref, rsqgl_params, save_params, outlier_thresh, max_raw_cpts,
+               min_event_to_seq_ratio, const_scale, skip_seq_scaling, seq_samp_type,
+               max_scaling_iters, worker_policy, subsample_seed, device):
+    ctx = _lib.get_context(device)
+    _ensure_model(ctx, std_ref)
+    n = len(map_results)
+    raw, raw_off, seq, seq_off = pack_reads(map_results)
     # worker_policy: RNA flip + stall detection + iterate + rescue happen in the
     # library; otherwise exactly one resquiggle_read call on the data as given
     is_rna_worker = worker_policy and seq_samp_type.name == RNA_SAMP_TYPE
@@ -213,7 +240,7 @@ def _run_batch(map_results, std_ref, rsqgl_params, save_params, outlier_thresh, 
     for i, mr in enumerate(map_results):
         st = int(res['status'][i])
         if st != 0:
-            out.append(th.TomboError(_lib.status_message(st)))
+            out.append(_status_exception(st))
             continue
         a, b = res['seg_off'][i], res['seg_off'][i + 1]
         segs = res['segs'][a:b].copy()

@@ -7,6 +7,8 @@ section 2, row 8)."""
 import re
 from collections import namedtuple
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -279,19 +281,31 @@ def new_fast5_group_layout(rsqgl_res, norm_type, event_data, rna=False, alignVal
     return attrs, aln, datasets, [('read_start_rel_to_raw', rsqgl_res.read_start_rel_to_raw)]
 
 
+def _is_hdf5_like(obj):
+    """an already-open HDF5 file object (h5py.File or a stand-in with its interface)"""
+    return hasattr(obj, 'create_group') or (hasattr(obj, '__getitem__') and hasattr(obj, 'attrs'))
+
+
 def write_new_fast5_group(fast5_data, corr_grp_slot, rsqgl_res, norm_type, compute_sd,
                           alignVals=None, old_segs=None, rna=False, norm_means=None,
                           norm_stds=None):
-    """tombo_helper.py:2341-2460 over any h5py-like object (``fast5_data`` may be an open
-    ``h5py.File`` or a path; h5py itself is outside this package's requirements)."""
-    event_data = events_table(rsqgl_res, compute_sd, norm_means, norm_stds)
+    """tombo_helper.py:2341-2460 over any h5py-like object.  Like the reference, anything
+    that is not an open file object (str, bytes, os.PathLike ...) is opened here with h5py
+    (h5py itself is outside this package's requirements) and closed again on every path."""
+    try:
+        event_data = events_table(rsqgl_res, compute_sd, norm_means, norm_stds)
+    except TomboError:
+        raise
+    except Exception:
+        raise TomboError('Error computing new events')          # tombo_helper.py:2364-2366
     attrs, aln, datasets, ev_attrs = new_fast5_group_layout(
         rsqgl_res, norm_type, event_data, rna, alignVals, old_segs)
     do_close = False
-    if isinstance(fast5_data, str):
+    if not _is_hdf5_like(fast5_data):
         try:
             import h5py
-            fast5_data = h5py.File(fast5_data, 'r+')
+            fn = os.fsdecode(fast5_data) if isinstance(fast5_data, (bytes, os.PathLike)) else fast5_data
+            fast5_data = h5py.File(fn, 'r+')
             do_close = True
         except Exception:
             raise TomboError('Error opening file for new group writing. This should have '
@@ -299,24 +313,27 @@ def write_new_fast5_group(fast5_data, corr_grp_slot, rsqgl_res, norm_type, compu
                              'no other tombo processes or processes accessing these HDF5 '
                              'files running simultaneously.')
     try:
-        corr_subgrp = fast5_data['/Analyses'][corr_grp_slot].create_group(
-            rsqgl_res.align_info.Subgroup)
-        for k, v in attrs:
-            corr_subgrp.attrs[k] = v
-        corr_alignment = corr_subgrp.create_group('Alignment')
-        for k, v in aln:
-            corr_alignment.attrs[k] = v
-        for name, data in datasets:
-            if name == 'Events':
-                ds = corr_subgrp.create_dataset('Events', data=data, compression='gzip')
-                for k, v in ev_attrs:
-                    ds.attrs[k] = v
-            else:
-                corr_alignment.create_dataset(name.split('/', 1)[1], data=data, compression='gzip')
-    except Exception:
-        raise TomboError('Error writing resquiggle information back into fast5 file.')
-    if do_close:
         try:
-            fast5_data.close()
+            corr_subgrp = fast5_data['/Analyses'][corr_grp_slot].create_group(
+                rsqgl_res.align_info.Subgroup)
+            for k, v in attrs:
+                corr_subgrp.attrs[k] = v
+            corr_alignment = corr_subgrp.create_group('Alignment')
+            for k, v in aln:
+                corr_alignment.attrs[k] = v
+            for name, data in datasets:
+                if name == 'Events':
+                    ds = corr_subgrp.create_dataset('Events', data=data, compression='gzip')
+                    for k, v in ev_attrs:
+                        ds.attrs[k] = v
+                else:
+                    corr_alignment.create_dataset(name.split('/', 1)[1], data=data,
+                                                  compression='gzip')
         except Exception:
-            raise TomboError('Error closing fast5 file after writing resquiggle information.')
+            raise TomboError('Error writing resquiggle information back into fast5 file.')
+    finally:
+        if do_close:
+            try:
+                fast5_data.close()
+            except Exception:
+                raise TomboError('Error closing fast5 file after writing resquiggle information.')

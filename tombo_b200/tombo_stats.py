@@ -267,45 +267,45 @@ def compute_num_events(signal_len, seq_len, mean_obs_per_event,
 # ---------------------------------------------------------------------------
 # per-read alternative-model statistics (tombo_stats.py:3888-4082)
 # ---------------------------------------------------------------------------
+def _slice_padded(seq, lo, hi):
+    """``seq[lo:hi]`` where positions outside the string read as 'N'"""
+    return 'N' * max(0, -lo) + seq[max(0, lo):max(0, min(len(seq), hi))] + 'N' * max(0, hi - len(seq))
+
+
 def trim_seq_and_means(seq, means, r_start, reg_start, reg_end, strand, kmer_width,
                        central_pos, max_motif_bb, max_motif_ab):
-    """tombo_stats.py:3888-3970"""
-    r_end = r_start + means.shape[0]
-    motif_search_seq = seq
-    num_start_clip, num_end_clip = 0, 0
-    if r_start + kmer_width - 1 < reg_start:
-        if strand == '+':
-            num_start_clip = reg_start - (r_start + kmer_width - 1)
-        else:
-            num_end_clip = reg_start - (r_start + kmer_width - 1)
-        r_start = reg_start - (kmer_width - 1)
-    if r_end - kmer_width + 1 > reg_end:
-        if strand == '+':
-            num_end_clip = r_end - kmer_width + 1 - reg_end
-        else:
-            num_start_clip = r_end - kmer_width + 1 - reg_end
-    seq = seq[num_start_clip:]
-    if num_end_clip > 0:
-        seq = seq[:-num_end_clip]
-    means = means[num_start_clip + central_pos:]
-    means = means[:-(num_end_clip + kmer_width - central_pos - 1)]
-    if means.shape[0] < kmer_width:
+    """Clip a read's sequence / base levels to a region (tombo_stats.py:3888-3970).
+
+    Returns ``(kmers, means, r_start, motif_search_seq)``: the k-mers and levels of the
+    positions that have a full k-mer inside ``[reg_start - (K-1), reg_end + (K-1))``, the
+    genome position of the first testable base, and the sequence window motif searches
+    run over (padded with 'N' where a motif would reach outside the read).
+
+    Everything is expressed through two overhangs -- how far the read sticks out of the
+    region on the genome's low and high side -- mapped to the read's 5' / 3' end by strand.
+    Two slicing quirks of the reference are kept on purpose (they decide which reads raise):
+    a zero-width trailing trim empties the array (``x[:-0]``)."""
+    flank = kmer_width - 1
+    low_over = max(0, reg_start - (r_start + flank))
+    high_over = max(0, (r_start + means.shape[0] - flank) - reg_end)
+    clip5, clip3 = (low_over, high_over) if strand == '+' else (high_over, low_over)
+    if low_over > 0:
+        r_start = reg_start - flank
+    trimmed_seq = seq[clip5:max(0, len(seq) - clip3)]
+    tail = clip3 + kmer_width - central_pos - 1
+    trimmed_means = means[clip5 + central_pos:]
+    trimmed_means = trimmed_means[:max(0, trimmed_means.shape[0] - tail)] if tail else trimmed_means[:0]
+    if trimmed_means.shape[0] < kmer_width:
         raise th.TomboError('Read sequence too short in this region.')
-    kmers = th.get_seq_kmers(seq, kmer_width)
-    if len(kmers) != means.shape[0]:
+    kmers = th.get_seq_kmers(trimmed_seq, kmer_width)
+    if len(kmers) != trimmed_means.shape[0]:
         raise th.TomboError('Mismatching k-mer and mean levels.')
-    r_start += kmer_width - 1
-    if num_start_clip + kmer_width - 1 - max_motif_bb >= 0:
-        motif_search_seq = motif_search_seq[num_start_clip + kmer_width - 1 - max_motif_bb:]
-    else:
-        motif_search_seq = 'N' * -(
-            num_start_clip + kmer_width - 1 - max_motif_bb) + motif_search_seq
-    if num_end_clip + kmer_width - 1 - max_motif_ab >= 0:
-        motif_search_seq = motif_search_seq[:-(num_end_clip + kmer_width - 1 - max_motif_ab)]
-    else:
-        motif_search_seq = motif_search_seq + 'N' * -(
-            num_end_clip + kmer_width - 1 - max_motif_ab)
-    return kmers, means, r_start, motif_search_seq
+    # motif window: from max_motif_bb bases before the first testable base to
+    # max_motif_ab bases after the last one
+    lead = clip5 + flank - max_motif_bb
+    trail = clip3 + flank - max_motif_ab
+    window = _slice_padded(seq, lead, len(seq) - trail) if trail else ''
+    return kmers, trimmed_means, r_start + flank, window
 
 
 def compute_alt_model_read_stats(r_data, std_ref, alt_refs, use_standard_llhr=False,
