@@ -306,6 +306,64 @@ int tb2_calc_llh_ratio_windows(tb2_ctx *ctx, int mode, int64_t n_sites, int kmer
                                double height_factor, double height_power,
                                double *llr_out);
 
+/* ---- per-read statistics on the RESIDENT batch (after tb2_batch_compute) -------------
+ * compute_alt_model_read_stats (tombo_stats.py:3972-4082) for every successfully
+ * resquiggled read of the batch without leaving HBM: sequence, per-base means and status
+ * are already there.  read_start[n_reads] are the reads' genome start positions.  LLRs and
+ * positions stay on the device for tb2_region_stats_add_batch_llr; tb2_batch_llr_download
+ * copies them out (site_off has n_reads + 1 entries; llr_out / pos_out sized
+ * *n_sites_total). */
+int tb2_batch_alt_llr(tb2_ctx *ctx, const int64_t *read_start, int alt_base_code,
+                      int use_standard_llhr, double scale_factor, double height_factor,
+                      double height_power, int64_t *n_sites_total);
+int tb2_batch_llr_download(tb2_ctx *ctx, double *llr_out, int64_t *pos_out, int64_t *site_off);
+
+/* ---- per-position aggregation of per-read statistics -----------------
+ * collate_reg_stats tombo_stats.py:4124-4178 + apply_per_read_thresh :4084-4122 +
+ * calc_damp_fraction :2537-2552 for one region [reg_start, reg_start + reg_len) (the
+ * reference works in 10 kb blocks, :4591-4595).  begin zeroes three dense int32 counters
+ * per position (coverage, valid coverage, stats >= single_read_thresh); add* accumulate
+ * (NaN stats are dropped like :4130-4133; lower_thresh NaN <=> None; stat_type 0 =
+ * alternative-model LLR, 1 = de novo / sample compare); finalize returns the covered
+ * positions in ascending order with reg_frac_standard_base, the dampened fraction
+ * (unmod_count / mod_count pseudo counts, NaN unmod_count = skip), reg_cov and valid_cov.
+ * Counters are sums: reads of one region sharded over GPUs are combined by adding the
+ * arrays returned by tb2_region_counts_get (3 * reg_len int32) -- with NCCL / any
+ * all-reduce -- and storing the sum with tb2_region_counts_set before finalize. */
+int tb2_region_stats_begin(tb2_ctx *ctx, int64_t reg_start, int64_t reg_len);
+int tb2_region_stats_add(tb2_ctx *ctx, int64_t n, const double *stats, const int64_t *pos,
+                         double single_read_thresh, double lower_thresh, int stat_type);
+int tb2_region_stats_add_batch_llr(tb2_ctx *ctx, double single_read_thresh,
+                                   double lower_thresh, int stat_type);
+int tb2_region_counts_get(tb2_ctx *ctx, int32_t *counts);
+int tb2_region_counts_set(tb2_ctx *ctx, const int32_t *counts);
+int tb2_region_stats_finalize(tb2_ctx *ctx, double unmod_count, double mod_count, int64_t cap,
+                              int64_t *pos_out, double *frac_out, double *damp_frac_out,
+                              int64_t *cov_out, int64_t *valid_cov_out, int64_t *n_out);
+
+/* ---- de novo / sample-compare per-read tests -------------------------
+ * z = |mean - ref| / sd -> two-sided normal p -> windowed Fisher's method
+ * (calc_window_fishers_method tombo_stats.py:2252-2271; fm_offset 0 = plain p-values).
+ * tb2_window_fisher_pvals works on explicit level arrays cut into segments (seg_off has
+ * n_segs + 1 entries): the arithmetic of compute_sample_compare_read_stats (:3675-3769,
+ * final_clamp 0) and of compute_de_novo_read_stats (:3771-3873, final_clamp 1:
+ * np.maximum(p, SMALLEST_PVAL)).  Outputs have the inputs' length; the first / last
+ * fm_offset entries of a segment and entries with NaN inputs are NaN.  With ref_means and
+ * ref_sds both NULL, `means` holds p-values already (the bare Fisher window).  Floating point:
+ * erfc / log / exp of the device library, parity with scipy within rtol 1e-7.
+ * tb2_de_novo_read_stats_batch runs the de novo test for whole '+' strand reads with
+ * the canonical levels looked up on the device (tb2_set_model): stat_off (n_reads + 1,
+ * filled) counts n_bases - (kmer_width - 1) positions per read. */
+int tb2_window_fisher_pvals(tb2_ctx *ctx, int64_t n_segs, const double *means,
+                            const double *ref_means, const double *ref_sds,
+                            const int64_t *seg_off, int64_t fm_offset, int final_clamp,
+                            double *pvals_out);
+int tb2_de_novo_read_stats_batch(tb2_ctx *ctx, int64_t n_reads, const double *norm_mean,
+                                 const int64_t *mean_off, const uint8_t *seq,
+                                 const int64_t *seq_off, const int64_t *read_start,
+                                 int64_t fm_offset, double *pvals_out, int64_t *pos_out,
+                                 int64_t *stat_off);
+
 #ifdef __cplusplus
 }
 #endif

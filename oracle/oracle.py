@@ -404,3 +404,73 @@ def resquiggle_read(raw, rm, rs, params, pol, scale_values=None,
                    norm_params_changed=bool(res.norm_params_changed),
                    norm_signal=norm[:res.n_norm].copy())
     return out
+
+
+# ---------------------------------------------------------------- batch checker
+def levels_from_codes(codes, means, sds, k):
+    """expected levels of one read from its base codes (dense 4^k tables)"""
+    c = np.asarray(codes, dtype=np.int64)
+    nb = c.shape[0] - k + 1
+    kidx = np.zeros(max(nb, 0), dtype=np.int64)
+    for j in range(k):
+        kidx = kidx * 4 + c[j:j + nb]
+    return means[kidx], sds[kidx]
+
+
+def run_batch(raw, raw_off, seq, seq_off, means, sds, k, params, save_params, pol,
+              indices=None, threads=None):
+    """orc_run_read over reads `indices` of a flat batch (the C-ABI layout), on a thread
+    pool (ctypes releases the GIL; oracle.c keeps no state between calls).  read_index =
+    position in the batch, which keys the Theil-Sen sub-sampling like the library does.
+    Returns {index: result dict}."""
+    import os
+    from multiprocessing.pool import ThreadPool
+    lib()
+    if indices is None:
+        indices = range(raw_off.shape[0] - 1)
+    indices = [int(i) for i in indices]
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    threads = max(1, min(threads, 64, len(indices)))
+
+    def one(i):
+        rm, rs = levels_from_codes(seq[seq_off[i]:seq_off[i + 1]], means, sds, k)
+        r = np.asarray(raw[raw_off[i]:raw_off[i + 1]], dtype=np.float64)
+        return i, run_read(r, rm, rs, params, save_params, pol, read_index=i)
+    if threads == 1:
+        return dict(one(i) for i in indices)
+    with ThreadPool(threads) as tp:
+        return dict(tp.imap_unordered(one, indices, chunksize=max(1, len(indices) // (threads * 8))))
+
+
+def compare_batch(res, oracle_out):
+    """bit-compare a tb2_resquiggle_batch result dict with run_batch output.  Returns a
+    list of (read index, field) mismatches (empty = parity)."""
+    bad = []
+    for i, o in oracle_out.items():
+        if int(res['status'][i]) != o['status']:
+            bad.append((i, 'status %d != %d' % (int(res['status'][i]), o['status'])))
+            continue
+        if o['status'] != 0:
+            continue
+        a, b = int(res['seg_off'][i]), int(res['seg_off'][i + 1])
+        if not np.array_equal(res['segs'][a:b], o['segs']):
+            bad.append((i, 'segs'))
+        if int(res['read_start_rel_to_raw'][i]) != o['read_start_rel_to_raw']:
+            bad.append((i, 'read_start_rel_to_raw'))
+        sv = res['scale_values'][i]
+        for j, key in enumerate(('shift', 'scale', 'lower_lim', 'upper_lim')):
+            if not (sv[j] == o[key] or (np.isnan(sv[j]) and np.isnan(o[key]))):
+                bad.append((i, key))
+        if res['sig_match_score'][i] != o['sig_match_score']:
+            bad.append((i, 'sig_match_score'))
+        if int(res['n_iters'][i]) != o['n_iters']:
+            bad.append((i, 'n_iters'))
+        if bool(res['flags'][i] & 2) != o['rescued']:
+            bad.append((i, 'rescued'))
+        if bool(res['flags'][i] & 1) != o['norm_params_changed']:
+            bad.append((i, 'norm_params_changed'))
+    return bad

@@ -35,6 +35,17 @@ CONFIGS = {
     'dna_rescue': ('DNA', (4.2, 4.2, 120, 1500, 20.0, 40, 300, 2500, 100), 600, 6, 16000,
                    {'stall': True}),
     'rna_8k': ('RNA', None, 270, 6, 17000, {}),
+    # --- round 2: the shapes of BASELINE.json configs[2..4] ---
+    # configs[4]: 50k-sample reads, bandwidth 1200; read 2 carries a planted stall that leaves
+    # the 1200 band and is rescued with the save bandwidth (1500)
+    'dna_c5_bw1200': ('DNA', (4.2, 4.2, 1200, 1500, 20.0, 40, 750, 2500, 250), 5555, 3, 19000,
+                      {'stall_at': {2: (2500, 11000)}}),
+    # configs[2]: a 20k-sample bandwidth-400 read that only aligns with the save bandwidth
+    'dna_c3_rescue_long': ('DNA', (4.2, 4.2, 400, 1500, 20.0, 40, 750, 2500, 250),
+                           [2222, 2222, 1800], 3, 20000,
+                           {'stall_at': {0: (1200, 3500), 2: (900, 2500)}}),
+    # configs[3]: direct RNA, 8k samples, caller-supplied const_scale (median_const_scale branch)
+    'rna_const_scale': ('RNA', None, 270, 3, 21000, {'const_scale': 95.0}),
 }
 
 
@@ -48,15 +59,23 @@ def run_config(name):
                nbases=np.broadcast_to(np.asarray(nbases), (nreads,)).astype(np.int64),
                int16=bool(extra.get('int16')), stall=bool(extra.get('stall')))
     segs, seg_off, scal, msgs, chk = [], [0], [], [], []
+    stall_at = np.full((nreads, 2), -1, dtype=np.int64)
+    for i, v in extra.get('stall_at', {}).items():
+        stall_at[i] = v
+    out['stall_at'] = stall_at
+    out['const_scale'] = float(extra.get('const_scale', np.nan))
     for i in range(nreads):
         kw = {}
         if extra.get('int16'):
             kw['int16'] = True
         if extra.get('stall'):
             kw['stall'] = (300 + i, 1500)
+        if stall_at[i, 0] >= 0:
+            kw['stall'] = (int(stall_at[i, 0]), int(stall_at[i, 1]))
         r = syn.make_read(kmer_ref, cpos, int(out['nbases'][i]), seed0 + i, kind=kind, **kw)
         res, err, info = rh.run_read(r.raw, r.genome_seq, std_ref, sst, p, sp, read_index=i,
-                                     stable_ties=bool(extra.get('int16')))
+                                     stable_ties=bool(extra.get('int16')),
+                                     const_scale=extra.get('const_scale'))
         chk.append(float(np.sum(np.asarray(r.raw, dtype=np.float64))))
         if res is None:
             msgs.append(err)
@@ -136,25 +155,26 @@ def kernel_kats():
     return out
 
 
-def llr_config():
-    """compute_alt_model_read_stats on resquiggled synthetic DNA reads (5mC)."""
+def llr_config(kind='DNA', seed0=18000, nbases=300):
+    """compute_alt_model_read_stats on resquiggled synthetic reads (5mC alt model); DNA
+    (6-mers) or direct RNA (5-mers, BASELINE.json configs[3])."""
     m = rh.load_reference()
     th, ts = m['th'], m['ts']
-    kmer_ref, cpos = syn.make_kmer_ref('DNA', 0)
+    kmer_ref, cpos = syn.make_kmer_ref(kind, 0)
     alt_rows = syn.make_alt_kmer_ref(kmer_ref, 'C', seed=1)
     std_ref, alt_ref = rh.make_models(kmer_ref, cpos, alt_rows, 'C')
-    sst, p, sp = rh.make_params('DNA', CONFIGS['dna_static4k'][1])
-    out = dict(seed0=18000, nreads=4, nbases=300)
+    sst, p, sp = rh.make_params(kind, CONFIGS['dna_static4k'][1] if kind == 'DNA' else None)
+    out = dict(seed0=seed0, nreads=4, nbases=nbases, kind=kind)
     llr_s, llr_p, pos, off = [], [], [], [0]
     for i in range(4):
-        r = syn.make_read(kmer_ref, cpos, 300, 18000 + i)
+        r = syn.make_read(kmer_ref, cpos, nbases, seed0 + i, kind=kind)
         res, err, info = rh.run_read(r.raw, r.genome_seq, std_ref, sst, p, sp, read_index=i)
         assert res is not None
         norm_mean = ts.compute_base_means(res.raw_signal, res.segs)
         bases = np.array(list(res.genome_seq), dtype='S1')
         r_data = th.readData(start=1000 * i, end=1000 * i + len(res.genome_seq), filtered=False,
                              read_start_rel_to_raw=0, strand='+', fn='x', corr_group='g',
-                             rna=False)
+                             rna=(kind == 'RNA'))
         orig = (th.get_multiple_slots_read_centric, th.get_raw_read_slot)
         from unittest import mock
         th.get_multiple_slots_read_centric = lambda *a, **k: (norm_mean, bases)
@@ -189,3 +209,7 @@ if __name__ == '__main__':
     if not only or 'llr' in only:
         np.savez_compressed(os.path.join(HERE, 'llr_5mc.npz'), **llr_config())
         print('llr done')
+    if not only or 'llr_rna' in only:
+        np.savez_compressed(os.path.join(HERE, 'llr_rna_5mc.npz'),
+                            **llr_config('RNA', seed0=22000, nbases=270))
+        print('llr_rna done')

@@ -7,7 +7,9 @@ from tombo_b200 import synthetic as syn
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 READ_CONFIGS = ['dna_static4k', 'dna_adapt4k', 'dna_adapt_bw400', 'dna_long_subsample',
-                'dna_int16_stable', 'dna_rescue', 'rna_8k']
+                'dna_int16_stable', 'dna_rescue', 'rna_8k',
+                # round 2: BASELINE.json configs[2..4] shapes
+                'dna_c5_bw1200', 'dna_c3_rescue_long', 'rna_const_scale']
 RNA_ALN = (6, 4, 500, 1500, 20.0, 50, 1000, 3000, 250)
 DNA_SEG, RNA_SEG = (5, 3, 1, 5), (12, 6, 2, 15)
 
@@ -26,11 +28,19 @@ def reads_of(g):
             kw['int16'] = True
         if bool(g['stall']):
             kw['stall'] = (300 + i, 1500)
+        if 'stall_at' in g.files and int(g['stall_at'][i, 0]) >= 0:
+            kw['stall'] = (int(g['stall_at'][i, 0]), int(g['stall_at'][i, 1]))
         r = syn.make_read(kmer_ref, cpos, int(g['nbases'][i]), int(g['seed0']) + i, kind=kind, **kw)
         assert float(np.sum(np.asarray(r.raw, dtype=np.float64))) == float(g['raw_checksum'][i]), \
             'synthetic generator drifted from the golden inputs'
         reads.append(r)
     return kind, kmer_ref, cpos, reads
+
+
+def const_scale_of(g):
+    if 'const_scale' in g.files and not np.isnan(float(g['const_scale'])):
+        return float(g['const_scale'])
+    return None
 
 
 def params_of(g, RP):

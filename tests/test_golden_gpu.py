@@ -29,7 +29,8 @@ def test_batch_reproduces_reference(ctx, RPcls, name):
     means, sds = syn.kmer_table(kmer_ref)
     ctx.set_model(means, sds, len(kmer_ref[0][0]), cpos)
     raw, raw_off, seq, seq_off = _flatten(reads)
-    res = ctx.resquiggle_batch(raw, raw_off, seq, seq_off, rp, sp, _lib.make_policy(kind))
+    res = ctx.resquiggle_batch(raw, raw_off, seq, seq_off, rp, sp,
+                               _lib.make_policy(kind, const_scale=gu.const_scale_of(g)))
     for i in range(len(reads)):
         e = gu.expected(g, i)
         assert _lib.status_message(res['status'][i]) == e['message'], i
@@ -73,27 +74,36 @@ def test_kernel_known_answers(ctx):
     assert st == 0 and np.array_equal(cp, k['h_cpts_t'])
 
 
-def test_alt_model_llr_matches_reference(ctx, RPcls):
+@pytest.mark.parametrize('gname', ['llr_5mc', 'llr_rna_5mc'])
+def test_alt_model_llr_matches_reference(ctx, RPcls, gname):
+    """per-read 5mC LLRs of resquiggled reads == compute_alt_model_read_stats of the
+    reference (tombo_stats.py:3972-4082); DNA 6-mer and direct-RNA 5-mer models."""
     from tombo_b200 import _lib, synthetic as syn
-    g = gu.load('llr_5mc')
-    kmer_ref, cpos = syn.make_kmer_ref('DNA', 0)
+    g = gu.load(gname)
+    kind = str(g['kind']) if 'kind' in g.files else 'DNA'
+    kmer_ref, cpos = syn.make_kmer_ref(kind, 0)
+    K = len(kmer_ref[0][0])
     alt_rows = syn.make_alt_kmer_ref(kmer_ref, 'C', seed=1)
     means, sds = syn.kmer_table(kmer_ref)
-    alt = np.full((4 ** 6, 6), np.nan)
+    alt = np.full((4 ** K, K), np.nan)
     code = {'A': 0, 'C': 1, 'G': 2, 'T': 3}
     for km, pos, m, sd in alt_rows:
         idx = 0
         for b in km:
             idx = idx * 4 + code[b]
         alt[idx, pos] = m
-    ctx.set_model(means, sds, 6, cpos)
-    ctx.set_alt_model(alt, 6)
-    aln = (4.2, 4.2, 200, 1500, 20.0, 40, 750, 2500, 250)
-    rp, sp = RPcls(aln), RPcls(aln, save=True)
-    reads = [syn.make_read(kmer_ref, cpos, int(g['nbases']), int(g['seed0']) + i)
+    ctx.set_model(means, sds, K, cpos)
+    ctx.set_alt_model(alt, K)
+    if kind == 'DNA':
+        aln = (4.2, 4.2, 200, 1500, 20.0, 40, 750, 2500, 250)
+        rp, sp = RPcls(aln), RPcls(aln, save=True)
+    else:
+        rp = RPcls(gu.RNA_ALN, gu.RNA_SEG, rna=True)
+        sp = RPcls(gu.RNA_ALN, gu.RNA_SEG, rna=True, save=True)
+    reads = [syn.make_read(kmer_ref, cpos, int(g['nbases']), int(g['seed0']) + i, kind=kind)
              for i in range(int(g['nreads']))]
     raw, raw_off, seq, seq_off = _flatten(reads)
-    res = ctx.resquiggle_batch(raw, raw_off, seq, seq_off, rp, sp, _lib.make_policy('DNA'))
+    res = ctx.resquiggle_batch(raw, raw_off, seq, seq_off, rp, sp, _lib.make_policy(kind))
     assert (res['status'] == 0).all()
     read_start = np.arange(len(reads), dtype=np.int64) * 1000
     for std, key in ((False, 'llr_scaled'), (True, 'llr_standard')):

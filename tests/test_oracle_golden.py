@@ -11,7 +11,7 @@ def test_oracle_reproduces_reference_reads(orc, RPcls, name):
     g = gu.load(name)
     kind, kmer_ref, cpos, reads = gu.reads_of(g)
     rp, sp = gu.params_of(g, RPcls)
-    pol = orc.policy(kind)
+    pol = orc.policy(kind, const_scale=gu.const_scale_of(g))
     for i, r in enumerate(reads):
         rm, rsd = gu.levels(r.genome_seq, kmer_ref)
         o = orc.run_read(np.asarray(r.raw, dtype=np.float64), rm, rsd, rp, sp, pol, read_index=i)

@@ -45,3 +45,6 @@ SHIFT_CHANGE_THRESH = 0.1                  # :169
 SCALE_CHANGE_THRESH = 0.1                  # :170
 MAX_SCALING_ITERS = 3                      # :171
 MAX_POINTS_FOR_THEIL_SEN = 1000            # :178
+FM_OFFSET_DEFAULT = 1                      # :136
+SMALLEST_PVAL = 1e-50                      # :158
+COV_DAMP_COUNTS = [2, 0]                   # (unmodified, modified pseudo counts)

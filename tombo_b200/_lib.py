@@ -552,6 +552,114 @@ class Context(object):
         return llr[:tot].copy(), pos[:tot].copy(), site_off
 
 
+    # ---- per-read statistics on the resident batch / SURVEY 8(f) ----------
+    def batch_alt_llr(self, read_start, alt_base_code, use_standard_llhr=False,
+                      scale_factor=4.0, height_factor=1.0, height_power=0.2):
+        """LLRs of the resident batch (after batch_compute); returns the site count"""
+        read_start = as_i64(read_start)
+        tot = i64(0)
+        fn = self.lib.tb2_batch_alt_llr
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(read_start, i64), C.c_int(alt_base_code),
+                      C.c_int(int(bool(use_standard_llhr))), f64(scale_factor),
+                      f64(height_factor), f64(height_power), C.byref(tot)))
+        self._llr_total, self._llr_reads = int(tot.value), read_start.shape[0]
+        return self._llr_total
+
+    def batch_llr_download(self):
+        llr = np.empty(max(1, self._llr_total))
+        pos = np.empty(max(1, self._llr_total), dtype=np.int64)
+        site_off = np.zeros(self._llr_reads + 1, dtype=np.int64)
+        fn = self.lib.tb2_batch_llr_download
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(llr, f64), ptr(pos, i64), ptr(site_off, i64)))
+        return llr[:self._llr_total], pos[:self._llr_total], site_off
+
+    def region_stats_begin(self, reg_start, reg_len):
+        fn = self.lib.tb2_region_stats_begin
+        fn.restype = C.c_int
+        self.check(fn(self.handle, i64(int(reg_start)), i64(int(reg_len))))
+        self._reg_len = int(reg_len)
+
+    def region_stats_add(self, stats, pos, single_read_thresh, lower_thresh=None, stat_type=0):
+        stats, pos = as_f64(stats), as_i64(pos)
+        fn = self.lib.tb2_region_stats_add
+        fn.restype = C.c_int
+        self.check(fn(self.handle, i64(stats.shape[0]), ptr(stats, f64), ptr(pos, i64),
+                      f64(single_read_thresh),
+                      f64(float('nan') if lower_thresh is None else lower_thresh),
+                      C.c_int(stat_type)))
+
+    def region_stats_add_batch_llr(self, single_read_thresh, lower_thresh=None, stat_type=0):
+        fn = self.lib.tb2_region_stats_add_batch_llr
+        fn.restype = C.c_int
+        self.check(fn(self.handle, f64(single_read_thresh),
+                      f64(float('nan') if lower_thresh is None else lower_thresh),
+                      C.c_int(stat_type)))
+
+    def region_counts_get(self):
+        cnt = np.zeros(3 * self._reg_len, dtype=np.int32)
+        fn = self.lib.tb2_region_counts_get
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(cnt, C.c_int32)))
+        return cnt
+
+    def region_counts_set(self, counts):
+        cnt = np.ascontiguousarray(counts, dtype=np.int32)
+        assert cnt.shape[0] == 3 * self._reg_len
+        fn = self.lib.tb2_region_counts_set
+        fn.restype = C.c_int
+        self.check(fn(self.handle, ptr(cnt, C.c_int32)))
+
+    def region_stats_finalize(self, unmod_count=None, mod_count=None):
+        cap = self._reg_len
+        pos = np.empty(cap, dtype=np.int64)
+        frac, damp = np.empty(cap), np.empty(cap)
+        cov, valid = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64)
+        n = i64(0)
+        fn = self.lib.tb2_region_stats_finalize
+        fn.restype = C.c_int
+        self.check(fn(self.handle, f64(float('nan') if unmod_count is None else unmod_count),
+                      f64(0.0 if mod_count is None else mod_count), i64(cap), ptr(pos, i64),
+                      ptr(frac, f64), ptr(damp, f64), ptr(cov, i64), ptr(valid, i64), C.byref(n)))
+        m = int(n.value)
+        return dict(pos=pos[:m].copy(), frac=frac[:m].copy(), damp_frac=damp[:m].copy(),
+                    cov=cov[:m].copy(), valid_cov=valid[:m].copy())
+
+    def window_fisher_pvals(self, means, ref_means, ref_sds, seg_off, fm_offset, final_clamp):
+        means = as_f64(means)
+        seg_off = as_i64(seg_off)
+        out = np.empty(max(1, means.shape[0]))
+        fn = self.lib.tb2_window_fisher_pvals
+        fn.restype = C.c_int
+        if ref_means is None:            # `means` are p-values: Fisher window only
+            prm = prs = None
+        else:
+            ref_means, ref_sds = as_f64(ref_means), as_f64(ref_sds)
+            prm, prs = ptr(ref_means, f64), ptr(ref_sds, f64)
+        self.check(fn(self.handle, i64(seg_off.shape[0] - 1), ptr(means, f64), prm,
+                      prs, ptr(seg_off, i64), i64(int(fm_offset)),
+                      C.c_int(int(bool(final_clamp))), ptr(out, f64)))
+        return out[:means.shape[0]]
+
+    def de_novo_read_stats_batch(self, norm_mean, mean_off, seq, seq_off, read_start, fm_offset=1):
+        norm_mean, mean_off = as_f64(norm_mean), as_i64(mean_off)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        seq_off, read_start = as_i64(seq_off), as_i64(read_start)
+        n = mean_off.shape[0] - 1
+        cap = max(1, norm_mean.shape[0])
+        pv = np.empty(cap)
+        pos = np.empty(cap, dtype=np.int64)
+        stat_off = np.zeros(n + 1, dtype=np.int64)
+        fn = self.lib.tb2_de_novo_read_stats_batch
+        fn.restype = C.c_int
+        self.check(fn(self.handle, i64(n), ptr(norm_mean, f64), ptr(mean_off, i64),
+                      ptr(seq, C.c_uint8), ptr(seq_off, i64), ptr(read_start, i64),
+                      i64(int(fm_offset)), ptr(pv, f64), ptr(pos, i64), ptr(stat_off, i64)))
+        t = int(stat_off[-1])
+        return pv[:t].copy(), pos[:t].copy(), stat_off
+
+
 def make_policy(kind='DNA', outlier_thresh=5.0, max_raw_cpts=200,
                 min_event_to_seq_ratio=1.1, max_scaling_iters=3,
                 skip_seq_scaling=False, const_scale=None, subsample_seed=0,

@@ -87,3 +87,18 @@ int tb2_launch_theil_sen(tb2_ctx *ctx, const BatchView &b, const StagePolicy &po
 int tb2_launch_finalize(tb2_ctx *ctx, const BatchView &b, const StagePolicy &pol, int first_call,
                         double *norm_mean_out, double *norm_signal_out);
 int tb2_launch_count_active(tb2_ctx *ctx, const BatchView &b, int *dev_counter);
+
+// device view of the resident batch's results for the per-read statistics that follow
+// the resquiggle (llr.cu, region_stats.cu); valid after tb2_batch_compute
+struct BatchResultView {
+    int n_reads;
+    long long total_bases;
+    const double *norm_mean;            // [sum B], offsets base_off
+    const long long *base_off, *seq_off;
+    const unsigned char *seq;
+    const int *status;                  // status[r * stride]
+    int stride;
+};
+int tb2_batch_result_view(tb2_ctx *ctx, BatchResultView *out);
+int tb2_region_accumulate_dev(tb2_ctx *ctx, long long n, const double *stats_dev,
+                              const long long *pos_dev, double thresh, double lower, int stat_type);

@@ -45,6 +45,9 @@ struct tb2_ctx {
     int64_t launches = 0;
     double last_ms_total = 0, last_ms_dp = 0, last_dp_launches = 0, last_dp_reads = 0;
     std::shared_ptr<void> batch;   // BatchHolder (pipeline.cu)
+    std::shared_ptr<void> region;  // RegionState (region_stats.cu)
+    long long resident_llr_sites = 0;   // tb2_batch_alt_llr: sites / reads of the resident LLRs
+    int resident_llr_reads = 0;
     // tb2_resquiggle_batch pipelines large batches over two lanes (child contexts with
     // their own stream and pools): H2D of chunk k+1 overlaps the kernels of chunk k
     std::vector<tb2_ctx *> lanes;
@@ -56,8 +59,8 @@ struct tb2_ctx {
     int kmer_width = 0, central_pos = 0, alt_kmer_width = 0;
     // generic scratch pool (named slots), grow-only
     // slots: 0-11 mirror calls, 12-49 batch arrays (pipeline.cu), 50-69 llr.cu,
-    // 70-79 per-warp scratch pools
-    std::vector<DevBuf> pool = std::vector<DevBuf>(96);
+    // 70-79 per-warp scratch pools, 80-109 region_stats.cu
+    std::vector<DevBuf> pool = std::vector<DevBuf>(128);
     // pinned host staging for small results
     void *pinned = nullptr;
     size_t pinned_cap = 0;

@@ -16,6 +16,8 @@ struct LlrArgs {
     const long long *mean_off, *seq_off, *read_start;
     const unsigned char *seq;
     const double *kmeans, *ksds, *alt;   // alt[code * K + pos]
+    const int *status;                   // resident batch: reads that failed hold no sites
+    int status_stride;
 };
 
 __device__ __forceinline__ int kmer_code(const unsigned char *bases, int K)
@@ -38,7 +40,8 @@ k_llr(LlrArgs a, int *counts, const long long *site_off, double *llr_out, long l
     // trimmed read sequence: base i = seq[so + cpos + i]
     const unsigned char *bases = a.seq + a.seq_off[r] + a.cpos;
     const double *means = a.norm_mean + mo;
-    const int testable = nb - 2 * (K - 1);      // len(motif_search_seq)
+    int testable = nb - 2 * (K - 1);            // len(motif_search_seq)
+    if (a.status && a.status[(size_t)r * a.status_stride] != TB2_OK) testable = 0;
     if (testable <= 0) { if (!FILL && tid == 0) counts[r] = 0; return; }
     const int per = (testable + 255) / 256;
     const int i0 = min(testable, tid * per), i1 = min(testable, i0 + per);
@@ -154,6 +157,7 @@ extern "C" int tb2_alt_model_llr_batch(tb2_ctx *ctx, int64_t n_reads, const doub
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_SOFF].p, seq_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_START].p, read_start, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     LlrArgs a;
+    a.status = nullptr; a.status_stride = 0;
     a.n_reads = n; a.K = ctx->kmer_width; a.cpos = ctx->central_pos; a.alt_code = alt_base_code;
     a.use_std = use_standard_llhr ? 1 : 0;
     a.sf = scale_factor; a.hf = height_factor; a.hp = height_power;
@@ -183,6 +187,120 @@ extern "C" int tb2_alt_model_llr_batch(tb2_ctx *ctx, int64_t n_reads, const doub
     TB2_CUDA_TRY(ctx, cudaMemcpyAsync(pos_out, P[L_POS].p, total * 8, cudaMemcpyDeviceToHost, s));
     TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return TB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the same scoring on the RESIDENT batch (after tb2_batch_compute): sequence, per-base
+// means and per-read status are already in HBM, LLRs and positions stay there for
+// tb2_region_stats_add_batch_llr / tb2_batch_llr_download
+// ---------------------------------------------------------------------------
+namespace {
+// exclusive scan of the per-read site counts (one block; n is a batch, <= ~1e6)
+__global__ void __launch_bounds__(1024) k_scan_sites(const int *cnt, long long *site_off, int n)
+{
+    __shared__ long long warp_tot[32];
+    __shared__ long long base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { base_s = 0; site_off[0] = 0; }
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+        const int i = c0 + tid;
+        long long v = i < n ? cnt[i] : 0, inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        long long before = 0, total = 0;
+        for (int q = 0; q < 32; ++q) { if (q < warp) before += warp_tot[q]; total += warp_tot[q]; }
+        if (i < n) site_off[i + 1] = base_s + before + inc;
+        __syncthreads();
+        if (tid == 0) base_s += total;
+        __syncthreads();
+    }
+}
+enum { L_RSTART = 63, L_RCNT, L_RSITEOFF, L_RLLR, L_RPOS, L_RTOTAL };
+}  // namespace
+
+extern "C" int tb2_batch_alt_llr(tb2_ctx *ctx, const int64_t *read_start, int alt_base_code,
+                                 int use_standard_llhr, double scale_factor, double height_factor,
+                                 double height_power, int64_t *n_sites_total)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!read_start || alt_base_code < 0 || alt_base_code > 3) return TB2_ERR_INVALID_ARG;
+    if (ctx->kmer_width <= 0 || ctx->alt_kmer_width != ctx->kmer_width) {
+        ctx->err = "standard and alternative models must be set with the same k-mer width";
+        return TB2_ERR_INVALID_ARG;
+    }
+    BatchResultView v;
+    if ((rc = tb2_batch_result_view(ctx, &v))) return rc;
+    const int n = v.n_reads;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    TB2_CUDA_TRY(ctx, P[L_RSTART].reserve((size_t)n * 8));
+    TB2_CUDA_TRY(ctx, P[L_RCNT].reserve((size_t)n * 4));
+    TB2_CUDA_TRY(ctx, P[L_RSITEOFF].reserve((size_t)(n + 1) * 8));
+    // every site is a base: the batch's base count bounds the site count (no size round trip)
+    TB2_CUDA_TRY(ctx, P[L_RLLR].reserve((size_t)v.total_bases * 8 + 8));
+    TB2_CUDA_TRY(ctx, P[L_RPOS].reserve((size_t)v.total_bases * 8 + 8));
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(P[L_RSTART].p, read_start, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    LlrArgs a;
+    a.n_reads = n; a.K = ctx->kmer_width; a.cpos = ctx->central_pos; a.alt_code = alt_base_code;
+    a.use_std = use_standard_llhr ? 1 : 0;
+    a.sf = scale_factor; a.hf = height_factor; a.hp = height_power;
+    a.norm_mean = v.norm_mean; a.mean_off = v.base_off; a.seq_off = v.seq_off;
+    a.read_start = P[L_RSTART].as<long long>();
+    a.seq = v.seq;
+    a.kmeans = ctx->model_means.as<double>(); a.ksds = ctx->model_sds.as<double>();
+    a.alt = ctx->alt_means.as<double>();
+    a.status = v.status; a.status_stride = v.stride;
+    k_llr<false><<<n, 256, 0, s>>>(a, P[L_RCNT].as<int>(), nullptr, nullptr, nullptr);
+    TB2_CHECK_LAUNCH(ctx);
+    k_scan_sites<<<1, 1024, 0, s>>>(P[L_RCNT].as<int>(), P[L_RSITEOFF].as<long long>(), n);
+    TB2_CHECK_LAUNCH(ctx);
+    k_llr<true><<<n, 256, 0, s>>>(a, nullptr, P[L_RSITEOFF].as<long long>(), P[L_RLLR].as<double>(),
+                                  P[L_RPOS].as<long long>());
+    TB2_CHECK_LAUNCH(ctx);
+    long long total = 0;
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(&total, P[L_RSITEOFF].as<long long>() + n, 8, cudaMemcpyDeviceToHost, s));
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    ctx->resident_llr_sites = total;
+    ctx->resident_llr_reads = n;
+    if (n_sites_total) *n_sites_total = total;
+    return TB2_OK;
+}
+
+extern "C" int tb2_batch_llr_download(tb2_ctx *ctx, double *llr_out, int64_t *pos_out, int64_t *site_off)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (ctx->resident_llr_reads <= 0 || !site_off) return TB2_ERR_INVALID_ARG;
+    auto &P = ctx->pool;
+    cudaStream_t s = ctx->stream;
+    const size_t t = (size_t)ctx->resident_llr_sites;
+    if (t && (!llr_out || !pos_out)) return TB2_ERR_INVALID_ARG;
+    TB2_CUDA_TRY(ctx, cudaMemcpyAsync(site_off, P[L_RSITEOFF].p, (size_t)(ctx->resident_llr_reads + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (t) {
+        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(llr_out, P[L_RLLR].p, t * 8, cudaMemcpyDeviceToHost, s));
+        TB2_CUDA_TRY(ctx, cudaMemcpyAsync(pos_out, P[L_RPOS].p, t * 8, cudaMemcpyDeviceToHost, s));
+    }
+    TB2_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return TB2_OK;
+}
+
+// the resident LLRs feed the region counters without leaving the device
+extern "C" int tb2_region_stats_add_batch_llr(tb2_ctx *ctx, double single_read_thresh,
+                                              double lower_thresh, int stat_type)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (ctx->resident_llr_reads <= 0 || isnan(single_read_thresh)) return TB2_ERR_INVALID_ARG;
+    return tb2_region_accumulate_dev(ctx, ctx->resident_llr_sites, ctx->pool[L_RLLR].as<double>(),
+                                     ctx->pool[L_RPOS].as<long long>(), single_read_thresh,
+                                     lower_thresh, stat_type);
 }
 
 extern "C" int tb2_new_mean_stds(tb2_ctx *ctx, const double *sig, int64_t n_sig,

@@ -522,6 +522,21 @@ static int batch_compute_impl(tb2_ctx *ctx, const tb2_params *params,
     return TB2_OK;
 }
 
+int tb2_batch_result_view(tb2_ctx *ctx, BatchResultView *out)
+{
+    BatchHolder *h = holder_of(ctx);
+    if (!h->computed) { ctx->err = "tb2_batch_compute has not been called"; return TB2_ERR_INVALID_ARG; }
+    out->n_reads = h->hb.n;
+    out->total_bases = h->hb.total_b;
+    out->norm_mean = ctx->pool[B_OUT_NORMMEAN].as<double>();
+    out->base_off = h->v.base_off;
+    out->seq_off = h->v.seq_off;
+    out->seq = h->v.seq;
+    out->status = &h->v.st[0].status;
+    out->stride = (int)(sizeof(ReadState) / sizeof(int));
+    return TB2_OK;
+}
+
 static int batch_download_impl(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_rel_to_raw,
                                   tb2_scale_values *scale_out, double *sig_match_score,
                                   double *norm_mean, double *norm_signal, int32_t *status,

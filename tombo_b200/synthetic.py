@@ -132,7 +132,7 @@ def bases_for_samples(n_samples, kind='DNA'):
 # Fast vectorised bulk generator (benchmark sized sets, e.g. 100k reads)
 # --------------------------------------------------------------------------
 def make_read_batch(kmer_ref, n_reads, n_bases, seed, kind='DNA', int16=False,
-                    leader=None, scale=None, offset=480.0):
+                    leader=None, scale=None, offset=480.0, stall_every=0, stall_extra=0):
     """Generate ``n_reads`` reads at once.
 
     Returns ``(raw_flat, raw_off, seq_codes_flat, seq_off)``: raw signal
@@ -165,6 +165,9 @@ def make_read_batch(kmer_ref, n_reads, n_bases, seed, kind='DNA', int16=False,
         kidx = kidx * 4 + codes[first + j]
     dwell = min_obs + rs.geometric(1.0 / (mean_dwell - min_obs),
                                    int(base_off[-1]))
+    if stall_every and stall_extra:
+        sel = np.arange(stall_every - 1, n_reads, stall_every)
+        dwell[base_off[sel] + nb[sel] // 2] += int(stall_extra)
     sig_per_read = np.add.reduceat(dwell, base_off[:-1]) + leader
     raw_off = np.concatenate([[0], np.cumsum(sig_per_read)]).astype(np.int64)
     total = int(raw_off[-1])

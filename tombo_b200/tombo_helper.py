@@ -17,7 +17,7 @@ from ._default_parameters import DNA_SAMP_TYPE, RNA_SAMP_TYPE  # noqa: F401
 __all__ = [
     'TomboError', 'readData', 'TomboMotif', 'resquiggleParams', 'startClipParams',
     'stallParams', 'resquiggleResults', 'alignInfo', 'genomeLocation', 'sequenceData',
-    'channelInfo', 'dpResults', 'scaleValues', 'seqSampleType', 'get_seq_kmers',
+    'channelInfo', 'dpResults', 'scaleValues', 'seqSampleType', 'regionStats', 'get_seq_kmers',
     'valid_cpts_w_cap', 'valid_cpts_w_cap_t_test', 'banded_traceback',
     'adaptive_banded_forward_pass', 'get_raw_read_slot', 'get_multiple_slots_read_centric']
 
@@ -109,6 +109,12 @@ class sequenceData(namedtuple('sequenceData', ('seq', 'id', 'mean_q_score'))):
 class channelInfo(namedtuple('channelInfo', (
         'offset', 'range', 'digitisation', 'number', 'sampling_rate'))):
     """tombo_helper.py:286"""
+
+
+class regionStats(namedtuple('regionStats', (
+        'reg_frac_standard_base', 'reg_poss', 'chrm', 'strand', 'start', 'reg_cov', 'ctrl_cov',
+        'valid_cov'))):
+    """Region statistics (tombo_helper.py:299-313)"""
 
 
 class seqSampleType(namedtuple('seqSampleType', ('name', 'rev_sig'))):

@@ -12,19 +12,23 @@ from . import _lib
 from . import tombo_helper as th
 from ._default_parameters import (
     ALGN_PARAMS_TABLE, SEG_PARAMS_TABLE, RNA_SAMP_TYPE, DNA_SAMP_TYPE,
-    MIN_EVENT_TO_SEQ_RATIO, OCLLHR_SCALE, OCLLHR_HEIGHT, OCLLHR_POWER, STALL_PARAMS)
+    MIN_EVENT_TO_SEQ_RATIO, OCLLHR_SCALE, OCLLHR_HEIGHT, OCLLHR_POWER, STALL_PARAMS,
+    FM_OFFSET_DEFAULT, SMALLEST_PVAL)
 
 __all__ = [
     'TomboModel', 'AltModel', 'normalize_raw_signal', 'compute_base_means',
     'get_read_seg_score', 'calc_kmer_fitted_shift_scale', 'load_resquiggle_parameters',
     'compute_num_events', 'get_dynamic_prog_params', 'identify_stalls',
-    'compute_alt_model_read_stats', 'trim_seq_and_means']
+    'compute_alt_model_read_stats', 'trim_seq_and_means', 'apply_per_read_thresh',
+    'collate_reg_stats', 'calc_damp_fraction', 'calc_window_fishers_method',
+    'compute_de_novo_read_stats', 'compute_sample_compare_read_stats']
 
 # E|N(0,1)| = sqrt(2 / pi); the reference evaluates scipy.stats.halfnorm.expect()
 # (tombo_stats.py:84), which returns this value
 HALF_NORM_EXPECTED_VAL = float(np.sqrt(2.0 / np.pi))
 STANDARD_MODEL_NAME = 'standard'
 CONST_SD_MODEL = True                     # tombo_stats.py:112
+SAMP_COMP_TXT, DE_NOVO_TXT, ALT_MODEL_TXT = 'sample_compare', 'de_novo', 'model_compare'   # :89-91
 NORM_TYPES = ('none', 'pA', 'pA_raw', 'median', 'robust_median', 'median_const_scale')
 _CODE = {'A': 0, 'C': 1, 'G': 2, 'T': 3}
 
@@ -369,3 +373,179 @@ def compute_alt_model_read_stats(r_data, std_ref, alt_refs, use_standard_llhr=Fa
         all_llhrs[alt_name] = llhrs
         all_poss[alt_name] = gen_poss
     return all_llhrs, all_poss, read_id
+
+
+# ---------------------------------------------------------------------------
+# per-position aggregation (tombo_stats.py:4084-4178, 2537-2552)
+# ---------------------------------------------------------------------------
+def _region_counts(stats, stat_locs, single_read_thresh, lower_thresh, stat_type, device=0):
+    """dense-counter aggregation of (position, statistic) pairs on the device"""
+    ctx = _lib.get_context(device)
+    stat_locs = np.asarray(stat_locs, dtype=np.int64)
+    lo, hi = int(stat_locs.min()), int(stat_locs.max())
+    ctx.region_stats_begin(lo, hi - lo + 1)
+    ctx.region_stats_add(stats, stat_locs, single_read_thresh, lower_thresh,
+                         0 if stat_type == ALT_MODEL_TXT else 1)
+    return ctx.region_stats_finalize()
+
+
+def apply_per_read_thresh(reg_base_stats, single_read_thresh, lower_thresh, stat_type,
+                          stat_locs, ctrl_cov=None):
+    """tombo_stats.py:4084-4122 -> (reg_frac_std_base, reg_cov, ctrl_cov, valid_cov).
+    ``reg_base_stats`` is the per-position list of statistic arrays the reference builds;
+    thresholds and counts run on the device."""
+    n_pos = len(reg_base_stats)
+    lens = np.array([b.shape[0] for b in reg_base_stats], dtype=np.int64)
+    flat = np.concatenate(reg_base_stats) if n_pos else np.zeros(0)
+    agg = _region_counts(flat, np.repeat(np.arange(n_pos, dtype=np.int64), lens),
+                         single_read_thresh, lower_thresh, stat_type) if flat.shape[0] else None
+    frac = np.full(n_pos, np.nan)
+    reg_cov = lens.copy()
+    valid_cov = np.zeros(n_pos, dtype=np.int64)
+    if agg is not None:
+        frac[agg['pos']] = agg['frac']
+        valid_cov[agg['pos']] = agg['valid_cov']
+    if stat_type == SAMP_COMP_TXT:
+        ctrl_cov = [ctrl_cov[pos] if ctrl_cov is not None and pos in ctrl_cov else 0
+                    for pos in stat_locs]
+    else:
+        ctrl_cov = [0] * int(np.asarray(stat_locs).shape[0])
+    return frac, reg_cov, ctrl_cov, valid_cov
+
+
+def collate_reg_stats(stats, stat_locs, read_ids, per_read_q, reg_data, single_read_thresh,
+                      lower_thresh, stat_type, stat_name, ctrl_cov):
+    """tombo_stats.py:4124-4178 -> :class:`tombo_helper.regionStats`.  The reference sorts
+    the region's (position, statistic) pairs and splits them per position; here the pairs
+    go to dense per-position counters on the device (a counting sort) and come back as the
+    covered positions in ascending order.  ``per_read_q`` (the per-read statistics writer)
+    is outside the hot path and must be None."""
+    if per_read_q is not None:
+        raise NotImplementedError('per-read statistics blocks are written by the reference')
+    stats = np.concatenate(stats)
+    stat_locs = np.concatenate(stat_locs).astype(np.int64)
+    keep = ~np.isnan(stats)
+    if not keep.any():
+        raise th.TomboError('No valid positions in this region.')
+    agg = _region_counts(stats, stat_locs, single_read_thresh, lower_thresh, stat_type)
+    locs_sorted = np.sort(stat_locs[keep])
+    if stat_type == SAMP_COMP_TXT:
+        cc = [ctrl_cov[pos] if ctrl_cov is not None and pos in ctrl_cov else 0
+              for pos in locs_sorted]
+    else:
+        cc = [0] * int(locs_sorted.shape[0])
+    return th.regionStats(agg['frac'], agg['pos'], reg_data.chrm, reg_data.strand,
+                          reg_data.start, agg['cov'], cc, agg['valid_cov'])
+
+
+def calc_damp_fraction(cov_damp_counts, fracs, valid_cov):
+    """tombo_stats.py:2537-2552 (elementwise; the device evaluates the same expression inside
+    tb2_region_stats_finalize for the fused path)"""
+    non_mod_counts = np.round(fracs * valid_cov)
+    return (non_mod_counts + cov_damp_counts['unmod']) / (
+        valid_cov + sum(list(cov_damp_counts.values())))
+
+
+# ---------------------------------------------------------------------------
+# SURVEY 8(f)-2: de novo / sample-compare per-read tests (tombo_stats.py:2252-2271,
+# 3675-3873)
+# ---------------------------------------------------------------------------
+def calc_window_fishers_method(pvals, lag):
+    """tombo_stats.py:2252-2271 on the device (1-D input): Fisher's method over a moving
+    window of 2 * lag + 1 p-values; NaN in the first / last ``lag`` positions."""
+    assert lag > 0, 'Invalid p-value window provided.'
+    pvals = np.asarray(pvals, dtype=np.float64)
+    if pvals.ndim != 1:
+        raise NotImplementedError('1-D p-value vectors only')
+    if pvals.shape[-1] < (lag * 2) + 1:
+        raise th.TomboError("P-values vector too short for Fisher's Method window compuation.")
+    return _lib.get_context().window_fisher_pvals(
+        pvals, None, None, np.array([0, pvals.shape[0]]), lag, False)
+
+
+def _clip_to_region(r_means, r_seq, read_start, read_end, strand, reg_start, reg_end, lo_lag,
+                    hi_lag):
+    """keep the part of a read whose statistics fall inside [reg_start, reg_end): the read may
+    stick out by its low / high lag (k-mer context + Fisher window)"""
+    low_over = max(0, reg_start - (read_start + lo_lag))
+    high_over = max(0, (read_end - hi_lag) - reg_end)
+    clip5, clip3 = (low_over, high_over) if strand == '+' else (high_over, low_over)
+    n = r_means.shape[0]
+    r_means = r_means[clip5:max(clip5, n - clip3)] if clip3 or clip5 else r_means
+    if r_seq is not None:
+        r_seq = r_seq[clip5:max(clip5, len(r_seq) - clip3)] if clip3 or clip5 else r_seq
+    if low_over:
+        read_start = reg_start - lo_lag
+    if high_over:
+        read_end = reg_end + hi_lag
+    return r_means, r_seq, read_start, read_end
+
+
+def compute_de_novo_read_stats(r_data, std_ref, fm_offset=FM_OFFSET_DEFAULT, reg_data=None):
+    """tombo_stats.py:3771-3873 -> ({'de_novo': p-values}, {'de_novo': positions}, read_id).
+    Read data arrive through ``tombo_helper.get_multiple_slots_read_centric`` /
+    ``get_raw_read_slot`` (the FAST5 seam); z-scores, p-values and the Fisher window run on
+    the device."""
+    reg_start = reg_data.start if reg_data is not None else r_data.start
+    reg_end = reg_data.end if reg_data is not None else r_data.end
+    dnstrm = std_ref.kmer_width - std_ref.central_pos - 1
+    begin_lag, end_lag = (std_ref.central_pos, dnstrm) if r_data.strand == '+' else \
+        (dnstrm, std_ref.central_pos)
+    r_means, r_seq = th.get_multiple_slots_read_centric(r_data, ['norm_mean', 'base'],
+                                                        r_data.corr_group)
+    try:
+        read_id = th.get_raw_read_slot(r_data).attrs.get('read_id')
+    except Exception:
+        read_id = getattr(r_data, 'read_id', None)
+    if r_means is None or r_seq is None:
+        raise th.TomboError('Read does not contain valid re-squiggled data.')
+    r_seq = b''.join(r_seq).decode() if not isinstance(r_seq, str) else r_seq
+    r_means, r_seq, read_start, read_end = _clip_to_region(
+        np.asarray(r_means, dtype=np.float64), r_seq, r_data.start, r_data.end, r_data.strand,
+        reg_start, reg_end, begin_lag + fm_offset, end_lag + fm_offset)
+    if len(r_seq) < std_ref.kmer_width:
+        raise th.TomboError('Read does not contain information in this region.')
+    r_ref_means, r_ref_sds = std_ref.get_exp_levels_from_seq(r_seq, r_data.strand == '-')
+    if r_data.strand == '-':
+        r_means = r_means[::-1]
+    r_means = r_means[begin_lag:r_means.shape[0] - end_lag] if end_lag else r_means[begin_lag:][:0]
+    read_start += begin_lag
+    read_end -= end_lag
+    if fm_offset > 0 and r_means.shape[0] < 2 * fm_offset + 1:
+        raise th.TomboError("P-values vector too short for Fisher's Method window compuation.")
+    r_pvals = _lib.get_context().window_fisher_pvals(
+        np.ascontiguousarray(r_means), r_ref_means, r_ref_sds, np.array([0, r_means.shape[0]]),
+        fm_offset, True)
+    return {DE_NOVO_TXT: r_pvals}, {DE_NOVO_TXT: np.arange(read_start, read_end)}, read_id
+
+
+def compute_sample_compare_read_stats(r_data, ctrl_means, ctrl_sds, fm_offset=FM_OFFSET_DEFAULT,
+                                      reg_data=None):
+    """tombo_stats.py:3675-3769 -> ({'sample_compare': p-values}, {...: positions}, read_id);
+    ``ctrl_means`` / ``ctrl_sds`` cover [reg_start - fm_offset, reg_end + fm_offset)."""
+    reg_start = reg_data.start if reg_data is not None else r_data.start
+    reg_end = reg_data.end if reg_data is not None else r_data.end
+    got = th.get_multiple_slots_read_centric(r_data, ['norm_mean'], r_data.corr_group)
+    r_means = got[0] if isinstance(got, (tuple, list)) else got
+    try:
+        read_id = th.get_raw_read_slot(r_data).attrs.get('read_id')
+    except Exception:
+        read_id = getattr(r_data, 'read_id', None)
+    if r_means is None:
+        raise th.TomboError('Read does not contain re-squiggled level means.')
+    r_means, _, read_start, read_end = _clip_to_region(
+        np.asarray(r_means, dtype=np.float64), None, r_data.start, r_data.end, r_data.strand,
+        reg_start, reg_end, fm_offset, fm_offset)
+    if r_data.strand == '-':
+        r_means = r_means[::-1]
+    a, b = read_start - reg_start + fm_offset, read_end - reg_start + fm_offset
+    cm, cs = np.asarray(ctrl_means[a:b], dtype=np.float64), np.asarray(ctrl_sds[a:b], dtype=np.float64)
+    with np.errstate(all='ignore'):
+        if np.sum(~np.isnan(np.abs(r_means - cm) / cs)) == 0:
+            raise th.TomboError('No valid z-scores in read.')
+    if fm_offset > 0 and r_means.shape[0] < 2 * fm_offset + 1:
+        raise th.TomboError("P-values vector too short for Fisher's Method window compuation.")
+    r_pvals = _lib.get_context().window_fisher_pvals(
+        np.ascontiguousarray(r_means), cm, cs, np.array([0, r_means.shape[0]]), fm_offset, False)
+    r_poss = np.where(~np.isnan(r_pvals))[0]
+    return {SAMP_COMP_TXT: r_pvals[r_poss]}, {SAMP_COMP_TXT: r_poss + read_start}, read_id
