@@ -306,6 +306,11 @@ int tb2_calc_llh_ratio_windows(tb2_ctx *ctx, int mode, int64_t n_sites, int kmer
                                double height_factor, double height_power,
                                double *llr_out);
 
+/* device stopwatch (CUDA events on the context's stream) around any sequence of calls on
+ * this context; stop synchronises and returns the elapsed milliseconds */
+int tb2_timer_start(tb2_ctx *ctx);
+int tb2_timer_stop(tb2_ctx *ctx, double *ms_out);
+
 /* ---- per-read statistics on the RESIDENT batch (after tb2_batch_compute) -------------
  * compute_alt_model_read_stats (tombo_stats.py:3972-4082) for every successfully
  * resquiggled read of the batch without leaving HBM: sequence, per-base means and status

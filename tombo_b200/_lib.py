@@ -172,6 +172,19 @@ class Context(object):
     def launch_count(self):
         return int(self.lib.tb2_launch_count(self.handle))
 
+    def timer_start(self):
+        fn = self.lib.tb2_timer_start
+        fn.restype = C.c_int
+        self.check(fn(self.handle))
+
+    def timer_stop(self):
+        """device milliseconds since timer_start (CUDA events on the library's stream)"""
+        ms = f64(0.0)
+        fn = self.lib.tb2_timer_stop
+        fn.restype = C.c_int
+        self.check(fn(self.handle, C.byref(ms)))
+        return float(ms.value)
+
     def last_timing(self):
         """(compute ms, DP-kernel ms, DP launches, reads summed over DP launches)"""
         out = (f64 * 4)()

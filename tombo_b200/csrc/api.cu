@@ -49,6 +49,7 @@ extern "C" void tb2_ctx_destroy(tb2_ctx *ctx)
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+    if (ctx->ev_t0) { cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -78,6 +79,33 @@ extern "C" int tb2_last_timing(tb2_ctx *ctx, double *out3 /* 4 values */)
     if (!ctx || !out3) return TB2_ERR_INVALID_ARG;
     out3[0] = ctx->last_ms_total; out3[1] = ctx->last_ms_dp; out3[2] = ctx->last_dp_launches;
     out3[3] = ctx->last_dp_reads;
+    return TB2_OK;
+}
+
+// device-side stopwatch on the context's stream (CUDA events): brackets any sequence of
+// library calls issued on this context
+extern "C" int tb2_timer_start(tb2_ctx *ctx)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!ctx->ev_t0) {
+        TB2_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev_t0));
+        TB2_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev_t1));
+    }
+    TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return TB2_OK;
+}
+
+extern "C" int tb2_timer_stop(tb2_ctx *ctx, double *ms_out)
+{
+    int rc = tb2_use(ctx);
+    if (rc) return rc;
+    if (!ctx->ev_t0 || !ms_out) return TB2_ERR_INVALID_ARG;
+    TB2_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    TB2_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_t1));
+    float ms = 0;
+    TB2_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+    *ms_out = ms;
     return TB2_OK;
 }
 
