@@ -43,8 +43,8 @@ def plan(p, n_em, nb):
     is_short = n_em < sbw + snb or nb < snb
     w_main = w_static if is_short else max(sbw, bw)
     smem_cells = L.emul_row_cells(w_main)
-    if not is_short and bw <= 512:
-        smem_cells = max(smem_cells, 2 * L.emul_row_cells(bw))
+    if not is_short and bw > 528:      # wide bands: lane-chunk engine rows (dp_row.cuh)
+        smem_cells = max(smem_cells, L.emul_row_cells(bw))
     tb = L.emul_tb_words(nb, w_static, n_em)
     grow = L.emul_row_cells(max(1, n_em))
     if not is_short:

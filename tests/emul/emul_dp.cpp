@@ -50,3 +50,10 @@ int emul_align_batch(int klass, int n_reads, const int *cpts, const double *em,
 size_t emul_tb_words(long long rows, long long W, long long drift) { return tb2_tb_words(rows, W, drift); }
 int emul_row_cells(long long W) { return tb2_row_cells(W); }
 }
+
+// tuning counters of the adaptive engines (meaningful when built with -DTB2_DP_COUNTERS)
+extern "C" void emul_dp_counters(unsigned long long *out8, int reset)
+{
+    for (int i = 0; i < 8; ++i) out8[i] = g_tb2_dp_counters[i];
+    if (reset) for (int i = 0; i < 8; ++i) g_tb2_dp_counters[i] = 0;
+}

@@ -37,7 +37,38 @@ CASES = [
     ('adapt4k', (4.2, 4.2, 200, 1500, 20.0, 40, 300, 2500, 100), [444, 444, 380], 2),
     ('adapt_bw400', (4.2, 4.2, 400, 1500, 20.0, 40, 750, 2500, 250), [900, 700], 2),
     ('adapt_bw120_narrow', (4.2, 4.2, 120, 1500, 20.0, 40, 300, 2500, 100), [500, 444], 0),
+    # the register engine's chunk widths 7 / 10 / 13 / 17 at their widest bands, the
+    # DNA / RNA default bandwidths, and a band too wide for it (lane-chunk engine)
+    ('abs_ch7_w218', (4.2, 4.2, 218, 1500, 20.0, 40, 300, 2500, 100), [500, 700], 2),
+    ('abs_ch10_w300', (4.2, 4.2, 300, 1500, 20.0, 40, 750, 2500, 250), [1300, 900], 2),
+    ('abs_ch10_w311', (4.2, 4.2, 311, 1500, 20.0, 40, 750, 2500, 250), [1100], 2),
+    ('abs_ch13_w404', (4.2, 4.2, 404, 1500, 20.0, 40, 750, 2500, 250), [1200], 2),
+    ('abs_ch17_w500', (4.2, 4.2, 500, 1500, 20.0, 40, 750, 2500, 250), [1300], 2),
+    ('abs_ch17_w528', (4.2, 4.2, 528, 1500, 20.0, 40, 750, 2500, 250), [1300], 2),
+    ('chunk_engine_w600', (4.2, 4.2, 600, 1500, 20.0, 40, 750, 2500, 250), [1300], 2),
 ]
+
+
+def test_band_edge_failures_match_oracle(orc, dna_model, RPcls):
+    """reads with a planted stall leave a 60-cell adaptive band: the traceback reports
+    'extends beyond bandwidth' (status 2) exactly where the oracle does"""
+    import emul
+    from tombo_b200 import synthetic as syn
+    kmer_ref, cpos = dna_model
+    means, sds = syn.kmer_table(kmer_ref)
+    rp = RPcls((4.2, 4.2, 60, 1500, 20.0, 40, 200, 2500, 80))
+    reads = [syn.make_read(kmer_ref, cpos, nb, 500 + i, stall=(250 + i, 200 + 150 * i))
+             for i, nb in enumerate([600, 600, 600, 600, 500, 700])]
+    ins = [_events(orc, r, means, sds, rp) for r in reads]
+    res = emul.align_batch(ins, rp, klass=2)
+    sts = []
+    for (cp, em, rm, rs), o in zip(ins, res):
+        st, segs, rsrtr, dbg, epb = orc.find_adaptive_base_assignment(cp, em, rp, rm, rs)
+        assert o['status'] == st
+        if st == 0:
+            assert np.array_equal(o['segs'], segs) and o['rsrtr'] == rsrtr
+        sts.append(st)
+    assert 2 in sts and 0 in sts
 
 
 @pytest.mark.parametrize('name,aln,nbs,klass', CASES)

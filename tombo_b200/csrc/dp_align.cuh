@@ -7,7 +7,7 @@
 // Static bands (short reads, start search, masked start) run on the wavefront
 // engine, adaptive rows on the lane-chunk engine (dp_row.cuh).
 #pragma once
-#include "dp_row.cuh"
+#include "dp_row2.cuh"
 
 // packed-move words per lane (lane-chunk layout) are instantiated for
 // {1,2,3,4,5,8,16}: band widths up to 16*16*32 = 8192 cells
@@ -259,9 +259,20 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     PassCtx pc;
     tb2_pc_defaults(pc, a, wr, c);
     pc.em = a.em + clip; pc.n_em = n_emc; pc.mso = mso;
-    if (!tb2_setup_geom(pc, wr, bw)) return TB2_ERR_CAPACITY;
-    const int wpl = tb2_wpl_of(pc.chunk);
-    if (wpl > TB2_MAX_WPL) return TB2_ERR_CAPACITY;
+    // adaptive rows: register engine (dp_row2.cuh) for bands up to 528 cells, the
+    // shared-memory lane-chunk engine for wider ones
+    const int ach = tb2_abs_chunk(bw);
+    int wpl;
+    if (ach) {
+        pc.W = bw; pc.chunk = 0;
+        pc.buf0 = tb2_wf_rowbuf(wr, bw);
+        if (pc.buf0 == nullptr) return TB2_ERR_CAPACITY;
+        wpl = tb2_abs_wpr(ach);
+    } else {
+        if (!tb2_setup_geom(pc, wr, bw)) return TB2_ERR_CAPACITY;
+        wpl = tb2_wpl_of(pc.chunk);
+        if (wpl > TB2_MAX_WPL) return TB2_ERR_CAPACITY;
+    }
     const int bes0 = (half_bw <= mso) ? 0 : mso - half_bw;
     const int t2 = (int)((double)(half_bw + 1) / epb);
     const int tmp_len = max(max(half_bw, TB2_MASK_BASES), t2) + 1;
@@ -310,22 +321,35 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     int amax = 0;
     st = tb2_wavefront_rows(pc, c, TB2_MODE_MASKED, mask_seq_len, rowbuf, tb_wf, &amax);
     if (st != TB2_OK) return st;
-    // last masked row -> lane-transposed buffer 1 (source and destination disjoint)
-    for (int j = lane; j < bw; j += 32) {
-        const int lj = j / pc.chunk;
-        pc.buf1[(j - lj * pc.chunk) * 32 + lj] = rowbuf[j];
-    }
-    __syncwarp();
-    int sel = 1;
-    // ---- adaptive rows :314-412 (lane-chunk engine) ----
-    st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_ADAPTIVE, mask_seq_len, nb, nb, &sel, &amax);
-    if (st != TB2_OK) return st;
-    int cur_event = amax + a.starts[nb - 1];
-    if (lane == 0) a.read_tb[nb] = cur_event + 1;
     const int thresh = (int)p.band_bound_thresh;
-    st = tb2_tb_seg_chunk_dyn(wpl, tb_chunk, a.starts, nb, mask_seq_len, bw, pc.chunk, thresh,
-                              &cur_event, a.read_tb);
-    if (st != TB2_OK) return st;
+    int cur_event;
+    if (ach) {
+        // ---- adaptive rows :314-412 (register engine; moves indexed from mask_seq_len) ----
+        st = tb2_adaptive_rows_abs_dyn(ach, pc, c, mask_seq_len, nb, nb, rowbuf, tb_chunk, &amax);
+        if (st != TB2_OK) return st;
+        __syncwarp();
+        cur_event = amax + a.starts[nb - 1];
+        if (lane == 0) a.read_tb[nb] = cur_event + 1;
+        st = tb2_tb_seg_abs_dyn(ach, tb_chunk, a.starts, nb, mask_seq_len, bw, thresh, &cur_event,
+                                a.read_tb);
+        if (st != TB2_OK) return st;
+    } else {
+        // last masked row -> lane-transposed buffer 1 (source and destination disjoint)
+        for (int j = lane; j < bw; j += 32) {
+            const int lj = j / pc.chunk;
+            pc.buf1[(j - lj * pc.chunk) * 32 + lj] = rowbuf[j];
+        }
+        __syncwarp();
+        int sel = 1;
+        // ---- adaptive rows :314-412 (lane-chunk engine) ----
+        st = tb2_run_rows_dyn(wpl, pc, c, TB2_MODE_ADAPTIVE, mask_seq_len, nb, nb, &sel, &amax);
+        if (st != TB2_OK) return st;
+        cur_event = amax + a.starts[nb - 1];
+        if (lane == 0) a.read_tb[nb] = cur_event + 1;
+        st = tb2_tb_seg_chunk_dyn(wpl, tb_chunk, a.starts, nb, mask_seq_len, bw, pc.chunk, thresh,
+                                  &cur_event, a.read_tb);
+        if (st != TB2_OK) return st;
+    }
     st = tb2_tb_seg_wf(tb_wf, wf_words_ll, a.starts, mask_seq_len, bw, thresh, &cur_event, a.read_tb);
     if (st != TB2_OK) return st;
     // _trim_traceback :754-764

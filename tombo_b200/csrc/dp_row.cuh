@@ -691,6 +691,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
             if (tq == 15 || t == t_end) {                                                       \
                 tbs[((t - t_begin) >> 4) * 32 + lane] = cw;                                     \
                 cw = 0u;                                                                        \
+                __syncwarp();                                                                   \
             }                                                                                   \
             ++j; ++ep;                                                                          \
         }
@@ -746,6 +747,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
                 tbs[((t - t_begin) >> 4) * 32 + lane] = cw;                                     \
                 cw = 0u;                                                                        \
             }                                                                                   \
+            if (tq == 15 || t == t_end) __syncwarp();                                           \
             ++j; ++ep;                                                                          \
         }
         if (lean && t + 15 <= t_hi) {
@@ -765,6 +767,9 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
                 tbp += 32;
                 rd_a += 128u; wr_a += 128u;
                 j += 16; ep += 16;
+                // the tail lane's writes to the chaining row trail lane 0's reads by >= 31
+                // cells: a barrier per 16-step group orders every such pair (racecheck-clean)
+                __syncwarp();
             }
             cw = 0u;
         }

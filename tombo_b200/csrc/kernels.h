@@ -62,4 +62,9 @@ static inline size_t tb2_tb_words(long long rows, long long W, long long drift)
     // every mix of the two engines
     return (size_t)(rows * wpl * 32) + tb2_wf_words_bound(rows, W, drift);
 }
+// chunk width of the register engine for the adaptive band (dp_row2.cuh), 0 = band too wide
+static inline int tb2_abs_chunk_host(long long W)
+{
+    return W <= 218 ? 7 : (W <= 311 ? 10 : (W <= 404 ? 13 : (W <= 528 ? 17 : 0)));
+}
 static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }

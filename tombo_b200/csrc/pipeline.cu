@@ -181,10 +181,15 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
             ++*n_long;
             // start search: one plain row; adaptive rows: four transposed rows when the
             // band is narrow enough for the fast path (<= 512 cells), else two
+            // adaptive rows up to 528 cells live in registers (dp_row2.cuh) and only the masked
+            // start rows need one plain row; wider bands keep two (four up to 512) transposed
+            // rows for the lane-chunk engine
             const long long bw_cells = tb2_row_cells(p.bandwidth);
+            const long long bw_pairs = tb2_abs_chunk_host(p.bandwidth) != 0
+                                           ? (p.bandwidth + 1) / 2
+                                           : (p.bandwidth <= 512 ? 2 * bw_cells : bw_cells);
             cl->smem_cells = std::max(cl->smem_cells,
-                                      tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2,
-                                                                        p.bandwidth <= 512 ? 2 * bw_cells : bw_cells)));
+                                      tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2, bw_pairs)));
             cl->tb_words = std::max(cl->tb_words, std::max(tb2_tb_words(nb, p.bandwidth, n_em + p.bandwidth),
                                                            tb2_tb_words(p.start_n_bases, p.start_bw, p.start_n_bases)));
             if (n_em >= p.start_save_bw + p.start_n_bases) {

@@ -717,7 +717,8 @@ __device__ int raw_window(RawCtx &c, int *new_segs)
 #define EXTRA_SIG_FACTOR 1.1
 
 __global__ void __launch_bounds__(128)
-k_resolve(BatchView b, tb2_params p, StagePolicy pol, double *pool, size_t cap, int *counter)
+k_resolve(BatchView b, tb2_params p, StagePolicy pol, double *pool, size_t cap, int *counter,
+          double *big_pool, unsigned long long big_cap, unsigned long long *big_used)
 {
     const int lane = threadIdx.x & 31;
     const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -790,9 +791,17 @@ k_resolve(BatchView b, tb2_params p, StagePolicy pol, double *pool, size_t cap, 
             c.mhz = c.winsor ? p.max_half_z_score : 0.0;
             if (c.L < 1) { st = TB2_ERR_UNEXPECTED; break; }
             const size_t need = (size_t)n_ev * c.L + 2 * (size_t)c.L + 8;
-            if (need > cap) { st = TB2_ERR_CAPACITY; break; }
-            c.fwd = scr;
-            c.cs = scr + (size_t)n_ev * c.L;
+            double *win = scr;
+            if (need > cap) {
+                // a window too large for the per-warp slab (e.g. a base carrying a 10k-sample
+                // stall, BASELINE configs[4]): bump-allocate from the overflow arena of this
+                // launch; only when that is exhausted too is the read a loud capacity failure
+                const unsigned long long off = atomicAdd(big_used, (unsigned long long)need);
+                if (off + need > big_cap) { st = TB2_ERR_CAPACITY; break; }
+                win = big_pool + off;
+            }
+            c.fwd = win;
+            c.cs = win + (size_t)n_ev * c.L;
             c.ld0 = (int *)(c.cs + c.L);
             c.ld1 = c.ld0 + c.L;
             // new segs land in out[a+1 .. z-1]
@@ -1360,17 +1369,25 @@ int tb2_launch_stalls(tb2_ctx *ctx, const BatchView &b)
 int tb2_launch_resolve(tb2_ctx *ctx, const BatchView &b, const tb2_params &p,
                        const StagePolicy &pol, size_t cap)
 {
-    enum { SLOT_RAWDP = 73, SLOT_CNT2 = 74 };
+    enum { SLOT_RAWDP = 73, SLOT_CNT2 = 74, SLOT_RAWBIG = 75 };
     const int warps_per_block = 4;
     int grid = ctx->sm_count * 8;
     const int max_useful = (b.n_reads + warps_per_block - 1) / warps_per_block;
     if (grid > max_useful) grid = max_useful > 0 ? max_useful : 1;
     const size_t slots = (size_t)grid * warps_per_block;
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_RAWDP].reserve(slots * cap * sizeof(double)));
-    TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT2].reserve(sizeof(int)));
-    TB2_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool[SLOT_CNT2].p, 0, sizeof(int), ctx->stream));
+    TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT2].reserve(16));
+    TB2_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool[SLOT_CNT2].p, 0, 16, ctx->stream));
+    // overflow arena for windows beyond the per-warp slab: a window is at most
+    // (2 * MAX_DEL_FIX_WINDOW + few) bases x its samples; sized from the longest read,
+    // 64 MB .. 2 GB
+    const unsigned long long big_cap = std::min<unsigned long long>(
+        (2ULL << 30) / 8, std::max<unsigned long long>((64ULL << 20) / 8, 24ULL * 64ULL * (unsigned long long)std::max(1, b.max_raw)));
+    TB2_CUDA_TRY(ctx, ctx->pool[SLOT_RAWBIG].reserve((size_t)big_cap * sizeof(double)));
     k_resolve<<<grid, warps_per_block * 32, 0, ctx->stream>>>(
-        b, p, pol, ctx->pool[SLOT_RAWDP].as<double>(), cap, ctx->pool[SLOT_CNT2].as<int>());
+        b, p, pol, ctx->pool[SLOT_RAWDP].as<double>(), cap, ctx->pool[SLOT_CNT2].as<int>(),
+        ctx->pool[SLOT_RAWBIG].as<double>(), big_cap,
+        (unsigned long long *)(ctx->pool[SLOT_CNT2].as<int>() + 2));
     TB2_CHECK_LAUNCH(ctx);
     return TB2_OK;
 }
