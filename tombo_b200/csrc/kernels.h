@@ -63,6 +63,9 @@ static inline size_t tb2_tb_words(long long rows, long long W, long long drift)
     return (size_t)(rows * wpl * 32) + tb2_wf_words_bound(rows, W, drift);
 }
 // chunk width of the register engine for the adaptive band (dp_row2.cuh), 0 = band too wide
+#if defined(__CUDACC__) || defined(TB2_EMUL)
+__host__ __device__
+#endif
 static inline int tb2_abs_chunk_host(long long W)
 {
     return W <= 218 ? 7 : (W <= 311 ? 10 : (W <= 404 ? 13 : (W <= 528 ? 17 : 0)));
