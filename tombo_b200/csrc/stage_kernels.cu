@@ -621,7 +621,7 @@ struct RawCtx {
     int n_ev, L, m;
     int winsor;
     double mhz;
-    double *fwd;         // n_ev x L
+    double *fwd;         // n_ev x L; on entry of raw_window row r holds the z-scores of base r
     double *cs;          // L
     int *ld0, *ld1;      // L each
 };
@@ -635,27 +635,52 @@ __device__ __forceinline__ double raw_z(const RawCtx &c, int row, int i)
     return z;
 }
 
+// all lanes: the z-scores of every (base, sample) cell of the window, written where the
+// forward values will go (the serial pass below consumes each one right before it overwrites
+// it) -- the IEEE divisions leave the single-lane critical path
+__device__ __forceinline__ void raw_fill_z(const RawCtx &c)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = 0; r < c.n_ev; ++r) {
+        double *row = c.fwd + (size_t)r * c.L;
+        for (int i = lane; i < c.L; i += 32) row[i] = raw_z(c, r, i);
+    }
+    __syncwarp();
+}
+
+// lane 0 only
 __device__ int raw_window(RawCtx &c, int *new_segs)
 {
     const int L = c.L, m = c.m, n_ev = c.n_ev;
     if (n_ev < 2 || L < 1) return TB2_ERR_UNEXPECTED;
-    // raw_forward_pass resquiggle.py:345-380 -- first row is a cumsum
+    // with raw_min_obs_per_base > 1 a row needs the cumulative z-scores of the row above
+    // (c_base_forward_pass :113, np.cumsum: sequential).  They are summed while that row is
+    // consumed -- same values, same order -- into one half of cs; the halves alternate.
+    const bool need_cs = m > 1;
+    double *cs_prev = c.cs, *cs_next = c.cs + L;
+    // raw_forward_pass resquiggle.py:345-380 -- first row is a cumsum of its z-scores
     {
         double acc = 0;
-        for (int i = 0; i < L; ++i) { acc = (i == 0) ? raw_z(c, 0, 0) : acc + raw_z(c, 0, i); c.fwd[i] = acc; c.ld0[i] = m; }
+        for (int i = 0; i < L; ++i) {
+            acc = (i == 0) ? c.fwd[0] : acc + c.fwd[i];
+            c.fwd[i] = acc; c.ld0[i] = m;
+            if (need_cs) cs_prev[i] = acc;
+        }
     }
     int *pld = c.ld0, *cld = c.ld1;
     for (int r = 1; r < n_ev; ++r) {
         const double *pf = c.fwd + (size_t)(r - 1) * L;
-        double *bf = c.fwd + (size_t)r * L;
+        double *bf = c.fwd + (size_t)r * L;      // holds z(r, .) until overwritten below
         // c_base_forward_pass :99-163; rows: start r*m, end r*m + L
         const int b_start = r * m, p_start = (r - 1) * m, p_end = p_start + L, b_end = b_start + L;
-        if (m > 1) {
-            double acc = 0;
-            for (int i = 0; i < L; ++i) { acc = (i == 0) ? raw_z(c, r - 1, 0) : acc + raw_z(c, r - 1, i); c.cs[i] = acc; }
-        }
+        double zacc = 0;
+        auto take_z = [&](int ix) {              // ix runs 0 .. L-1 in order over the row
+            const double zv = bf[ix];
+            if (need_cs) { zacc = (ix == 0) ? zv : zacc + zv; cs_next[ix] = zacc; }
+            return zv;
+        };
         if (b_start - p_start - 1 < 0 || b_start - p_start - 1 >= L) return TB2_ERR_UNEXPECTED;
-        bf[0] = raw_z(c, r, 0) + pf[b_start - p_start - 1];
+        bf[0] = take_z(0) + pf[b_start - p_start - 1];
         cld[0] = 1;
         for (int pos = b_start + 1; pos < p_end + 1; ++pos) {
             int lag = 1;
@@ -667,14 +692,14 @@ __device__ int raw_window(RawCtx &c, int *new_segs)
             double diag = pf[pos - p_start - lag];
             if (lag > 1) {
                 if (pos - p_start - 1 >= L) return TB2_ERR_UNEXPECTED;
-                diag += c.cs[pos - p_start - 1] - c.cs[pos - p_start - lag];
+                diag += cs_prev[pos - p_start - 1] - cs_prev[pos - p_start - lag];
             }
             if (pos - b_start >= L) return TB2_ERR_UNEXPECTED;
             const double stay = bf[pos - b_start - 1];
             double score; int dv;
             if (diag > stay) { score = diag; dv = 1; }
             else { score = stay; dv = cld[pos - b_start - 1] + 1; }
-            bf[pos - b_start] = raw_z(c, r, pos - b_start) + score;
+            bf[pos - b_start] = take_z(pos - b_start) + score;
             cld[pos - b_start] = dv;
         }
         if (b_end > p_end + 1) {
@@ -682,13 +707,14 @@ __device__ int raw_window(RawCtx &c, int *new_segs)
             int cl = cld[p_end - b_start];
             const int left = b_end - p_end - 1;
             for (int i = 0; i < left; ++i) {
-                fv += raw_z(c, r, i + p_end - b_start + 1);
+                fv += take_z(i + p_end - b_start + 1);
                 cl += 1;
                 bf[i + p_end - b_start + 1] = fv;
                 cld[i + p_end - b_start + 1] = cl;
             }
         }
         int *t = pld; pld = cld; cld = t;
+        double *tc = cs_prev; cs_prev = cs_next; cs_next = tc;
     }
     // raw_traceback resquiggle.py:382-400 with c_base_traceback :165-182
     int sig_start = (n_ev - 1) * m + L - 1;   // curr_end - 1
@@ -736,21 +762,14 @@ k_resolve(BatchView b, tb2_params p, StagePolicy pol, double *pool, size_t cap, 
         int *out = b.segs + bo + r;
         for (int i = lane; i <= nb; i += 32) out[i] = segs[i];
         __syncwarp();
-        if (lane != 0) continue;
         const int n_norm = segs[nb];
-        s.n_norm = n_norm;
+        if (lane == 0) s.n_norm = n_norm;
         const double *norm = b.norm + b.raw_off[r] + s.rsrtr;
         const double *rm = b.rm + bo, *rs = b.rs + bo;
         int *ws = b.starts + bo, *we = b.read_tb + bo + r;   // scratch (>= nb entries each)
         const int n_segs = nb + 1;
         const int m = (int)p.raw_min_obs_per_base;
         int nw = 0, st = TB2_OK;
-        for (int d = 0; d < nb; ++d) {                                   // :465-472
-            if (segs[d + 1] - segs[d] != 0) continue;
-            if (nw > 0 && d < we[nw - 1] + DEL_FIX_WINDOW) we[nw - 1] = d + DEL_FIX_WINDOW + 1;
-            else { ws[nw] = d - DEL_FIX_WINDOW; we[nw] = d + DEL_FIX_WINDOW + 1; ++nw; }
-        }
-        if (nw == 0) continue;
 #define TOO_SMALL(a, z) ((double)(segs[z] - segs[a]) <= ((double)(((z) - (a) + 1) * m)) * EXTRA_SIG_FACTOR)
 #define MERGE_TRIM() do { \
             int mm = 0; \
@@ -760,23 +779,37 @@ k_resolve(BatchView b, tb2_params p, StagePolicy pol, double *pool, size_t cap, 
             nw = mm; \
             if (ws[0] < 0) ws[0] = 0; \
             if (we[nw - 1] > n_segs - 1) we[nw - 1] = n_segs - 1; } while (0)
-        MERGE_TRIM();
-        int expanded = 0;
-        for (int it = 0; it < MAX_DEL_FIX_WINDOW - DEL_FIX_WINDOW; ++it) {   // :481-486
-            expanded = 0;
-            for (int k = 0; k < nw; ++k)
-                if (TOO_SMALL(ws[k], we[k])) { expanded = 1; ws[k] -= 1; we[k] += 1; }
-            if (!expanded) break;
-            MERGE_TRIM();
+        if (lane == 0) {
+            // the windows (lane 0; a handful of integers per read)
+            for (int d = 0; d < nb; ++d) {                                   // :465-472
+                if (segs[d + 1] - segs[d] != 0) continue;
+                if (nw > 0 && d < we[nw - 1] + DEL_FIX_WINDOW) we[nw - 1] = d + DEL_FIX_WINDOW + 1;
+                else { ws[nw] = d - DEL_FIX_WINDOW; we[nw] = d + DEL_FIX_WINDOW + 1; ++nw; }
+            }
+            if (nw > 0) {
+                MERGE_TRIM();
+                int expanded = 0;
+                for (int it = 0; it < MAX_DEL_FIX_WINDOW - DEL_FIX_WINDOW; ++it) {   // :481-486
+                    expanded = 0;
+                    for (int k = 0; k < nw; ++k)
+                        if (TOO_SMALL(ws[k], we[k])) { expanded = 1; ws[k] -= 1; we[k] += 1; }
+                    if (!expanded) break;
+                    MERGE_TRIM();
+                }
+                if (expanded)
+                    for (int k = 0; k < nw; ++k)
+                        if (TOO_SMALL(ws[k], we[k])) { st = TB2_ERR_NOT_ENOUGH_DEL_SIGNAL; break; }
+                if (st == TB2_OK && pol.max_raw_cpts >= 0) {
+                    int mx = 0;
+                    for (int k = 0; k < nw; ++k) mx = max(mx, we[k] - ws[k]);
+                    if (mx > pol.max_raw_cpts) st = TB2_ERR_TOO_MANY_DELS;
+                }
+            }
         }
-        if (expanded)
-            for (int k = 0; k < nw; ++k)
-                if (TOO_SMALL(ws[k], we[k])) { st = TB2_ERR_NOT_ENOUGH_DEL_SIGNAL; break; }
-        if (st == TB2_OK && pol.max_raw_cpts >= 0) {
-            int mx = 0;
-            for (int k = 0; k < nw; ++k) mx = max(mx, we[k] - ws[k]);
-            if (mx > pol.max_raw_cpts) st = TB2_ERR_TOO_MANY_DELS;
-        }
+        nw = __shfl_sync(TB2_FULL_MASK, nw, 0);
+        st = __shfl_sync(TB2_FULL_MASK, st, 0);
+        if (nw == 0) continue;
+        __syncwarp();                              // ws / we written by lane 0 are read by all
         for (int k = 0; k < nw && st == TB2_OK; ++k) {                    // :506-531
             const int a = ws[k], z = we[k], n_ev = z - a;
             const int sig_start = segs[a], sig_len = segs[z] - segs[a];
@@ -790,24 +823,31 @@ k_resolve(BatchView b, tb2_params p, StagePolicy pol, double *pool, size_t cap, 
             c.winsor = !isnan(p.max_half_z_score);
             c.mhz = c.winsor ? p.max_half_z_score : 0.0;
             if (c.L < 1) { st = TB2_ERR_UNEXPECTED; break; }
-            const size_t need = (size_t)n_ev * c.L + 2 * (size_t)c.L + 8;
-            double *win = scr;
+            const size_t need = (size_t)n_ev * c.L + 3 * (size_t)c.L + 8;
+            unsigned long long woff = 0;           // 0: the warp's own slab
             if (need > cap) {
                 // a window too large for the per-warp slab (e.g. a base carrying a 10k-sample
                 // stall, BASELINE configs[4]): bump-allocate from the overflow arena of this
                 // launch; only when that is exhausted too is the read a loud capacity failure
-                const unsigned long long off = atomicAdd(big_used, (unsigned long long)need);
-                if (off + need > big_cap) { st = TB2_ERR_CAPACITY; break; }
-                win = big_pool + off;
+                if (lane == 0) woff = atomicAdd(big_used, (unsigned long long)need) + 1ULL;
+                woff = __shfl_sync(TB2_FULL_MASK, woff, 0);
+                if (woff - 1ULL + need > big_cap) { st = TB2_ERR_CAPACITY; break; }
             }
+            double *win = woff ? big_pool + (woff - 1ULL) : scr;
             c.fwd = win;
-            c.cs = win + (size_t)n_ev * c.L;
-            c.ld0 = (int *)(c.cs + c.L);
+            c.cs = win + (size_t)n_ev * c.L;       // two halves of L
+            c.ld0 = (int *)(c.cs + 2 * (size_t)c.L);
             c.ld1 = c.ld0 + c.L;
+            raw_fill_z(c);                         // all lanes
             // new segs land in out[a+1 .. z-1]
-            st = raw_window(c, out + a + 1);
-            if (st == TB2_OK) for (int i = 0; i < n_ev - 1; ++i) out[a + 1 + i] += sig_start;
+            if (lane == 0) {
+                st = raw_window(c, out + a + 1);
+                if (st == TB2_OK) for (int i = 0; i < n_ev - 1; ++i) out[a + 1 + i] += sig_start;
+            }
+            st = __shfl_sync(TB2_FULL_MASK, st, 0);
+            __syncwarp();
         }
+        if (lane != 0) continue;
         if (st == TB2_OK) {
             for (int i = 0; i < nb; ++i) if (out[i + 1] - out[i] < 1) { st = TB2_ERR_ZERO_LEN_SEG; break; }
             if (st == TB2_OK && out[0] < 0) st = TB2_ERR_NEG_SEG;
@@ -1102,7 +1142,13 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                         const unsigned int slot = atomicAdd(&t.nbuf, 1u);
                         if (slot < QCAP) queue[slot] = ((unsigned int)i << 16) | (unsigned int)j;
                     };
+                    // fp32 images of ev that coincide (the reference's slope is then 1000.0) are
+                    // adjacent after the sort; a read without any takes the loops below without
+                    // the per-pair equality test (0.2 % of reads have one)
                     {
+                        int tie = 0;
+                        for (int i = tid; i + 1 < n; i += ST_THREADS) tie |= (t.pt[i].z == t.pt[i + 1].z);
+                        tie = __syncthreads_or(tie);
                         // thread c owns columns ja = c and jb = n - 1 - c (ja <= jb): rows
                         // i < ja are tested against both with one load of point i
                         const int half = (n + 1) / 2;
@@ -1112,6 +1158,51 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                             const float xla = pa.x + gLf, yha = pa.y - gHf;
                             const float xlb = pb.x + gLf, yhb = pb.y - gHf;
                             int i = 0;
+                            if (!tie) {
+                                // blocks of 32 rows: decided pairs are settled in registers, the
+                                // undecided ones only set a bit; the bits are queued after the
+                                // block, so the hot loop has no divergent branch
+                                if (ja != jb) {
+                                    for (; i + 32 <= ja; i += 32) {
+                                        uint32_t ua = 0u, ub = 0u;
+#pragma unroll
+                                        for (int k = 0; k < 32; ++k) {
+                                            const float4 pi = t.pt[i + k];
+                                            const bool la = pi.x > xla, ha = pi.y < yha;
+                                            const bool lb = pi.x > xlb, hb = pi.y < yhb;
+                                            below += la; below += lb;
+                                            if (!(la || ha)) ua |= 1u << k;
+                                            if (!(lb || hb)) ub |= 1u << k;
+                                        }
+                                        while (ua) { const int k = __ffs((int)ua) - 1; ua &= ua - 1u; push(i + k, ja); }
+                                        while (ub) { const int k = __ffs((int)ub) - 1; ub &= ub - 1u; push(i + k, jb); }
+                                    }
+                                    for (; i < ja; ++i) {
+                                        const float4 pi = t.pt[i];
+                                        const bool la = pi.x > xla, ha = pi.y < yha;
+                                        const bool lb = pi.x > xlb, hb = pi.y < yhb;
+                                        if (la || ha) below += la; else push(i, ja);
+                                        if (lb || hb) below += lb; else push(i, jb);
+                                    }
+                                }
+                                for (; i + 32 <= jb; i += 32) {
+                                    uint32_t ub = 0u;
+#pragma unroll
+                                    for (int k = 0; k < 32; ++k) {
+                                        const float4 pi = t.pt[i + k];
+                                        const bool lb = pi.x > xlb, hb = pi.y < yhb;
+                                        below += lb;
+                                        if (!(lb || hb)) ub |= 1u << k;
+                                    }
+                                    while (ub) { const int k = __ffs((int)ub) - 1; ub &= ub - 1u; push(i + k, jb); }
+                                }
+                                for (; i < jb; ++i) {
+                                    const float4 pi = t.pt[i];
+                                    const bool lb = pi.x > xlb, hb = pi.y < yhb;
+                                    if (lb || hb) below += lb; else push(i, jb);
+                                }
+                                continue;
+                            }
                             if (ja != jb) {
 #pragma unroll 4
                                 for (; i < ja; ++i) {
