@@ -43,7 +43,9 @@ def plan(p, n_em, nb):
     is_short = n_em < sbw + snb or nb < snb
     w_main = w_static if is_short else max(sbw, bw)
     smem_cells = L.emul_row_cells(w_main)
-    if not is_short and bw > 528:      # wide bands: lane-chunk engine rows (dp_row.cuh)
+    if not is_short and 528 < bw <= 1616:   # three chunks per lane (dp_row2.cuh)
+        smem_cells = max(smem_cells, 3 * (13 if bw <= 1236 else 17) * 32)
+    elif not is_short and bw > 1616:        # lane-chunk engine rows (dp_row.cuh)
         smem_cells = max(smem_cells, L.emul_row_cells(bw))
     tb = L.emul_tb_words(nb, w_static, n_em)
     grow = L.emul_row_cells(max(1, n_em))

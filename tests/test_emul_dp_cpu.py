@@ -45,7 +45,14 @@ CASES = [
     ('abs_ch13_w404', (4.2, 4.2, 404, 1500, 20.0, 40, 750, 2500, 250), [1200], 2),
     ('abs_ch17_w500', (4.2, 4.2, 500, 1500, 20.0, 40, 750, 2500, 250), [1300], 2),
     ('abs_ch17_w528', (4.2, 4.2, 528, 1500, 20.0, 40, 750, 2500, 250), [1300], 2),
-    ('chunk_engine_w600', (4.2, 4.2, 600, 1500, 20.0, 40, 750, 2500, 250), [1300], 2),
+    # wide bands: three chunks per lane (bandwidth 1200 of BASELINE configs[4], the save
+    # bandwidth 1500, the widest bands of both chunk widths), and the lane-chunk engine beyond
+    ('abs_ms13_w600', (4.2, 4.2, 600, 1500, 20.0, 40, 750, 2500, 250), [1300], 2),
+    ('abs_ms13_w1200', (4.2, 4.2, 1200, 1500, 20.0, 40, 750, 2500, 250), [1500], 2),
+    ('abs_ms13_w1236', (4.2, 4.2, 1236, 1500, 20.0, 40, 750, 2500, 250), [1600], 2),
+    ('abs_ms17_w1500', (4.2, 4.2, 1500, 1500, 20.0, 40, 750, 2500, 250), [2000], 2),
+    ('abs_ms17_w1616', (4.2, 4.2, 1616, 1500, 20.0, 40, 750, 2500, 250), [2200], 2),
+    ('chunk_engine_w1700', (4.2, 4.2, 1700, 1500, 20.0, 40, 750, 2500, 250), [2200], 2),
 ]
 
 

@@ -262,12 +262,16 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     // adaptive rows: register engine (dp_row2.cuh) for bands up to 528 cells, the
     // shared-memory lane-chunk engine for wider ones
     const int ach = tb2_abs_chunk(bw);
+    // three chunks per lane for bands up to 1616 cells when the warp's shared memory holds
+    // the slabs (2 * 3 * CH * 32 doubles)
+    int mch = ach ? 0 : tb2_abs_ms_chunk_host(bw);
+    if (mch && (wr.smem_cap < 2 * TB2_ABS_MS_SLABS * mch * 32 || !__isShared(wr.smem_rows))) mch = 0;
     int wpl;
-    if (ach) {
+    if (ach || mch) {
         pc.W = bw; pc.chunk = 0;
         pc.buf0 = tb2_wf_rowbuf(wr, bw);
         if (pc.buf0 == nullptr) return TB2_ERR_CAPACITY;
-        wpl = tb2_abs_wpr(ach);
+        wpl = tb2_abs_words_per_row(bw);
     } else {
         if (!tb2_setup_geom(pc, wr, bw)) return TB2_ERR_CAPACITY;
         wpl = tb2_wpl_of(pc.chunk);
@@ -332,6 +336,17 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
         if (lane == 0) a.read_tb[nb] = cur_event + 1;
         st = tb2_tb_seg_abs_dyn(ach, tb_chunk, a.starts, nb, mask_seq_len, bw, thresh, &cur_event,
                                 a.read_tb);
+        if (st != TB2_OK) return st;
+    } else if (mch) {
+        // ---- adaptive rows, wide band: three chunks per lane, state in shared memory ----
+        st = tb2_adaptive_rows_abs_ms_dyn(mch, pc, c, mask_seq_len, nb, nb, wr.smem_rows, rowbuf,
+                                          tb_chunk, &amax);
+        if (st != TB2_OK) return st;
+        __syncwarp();
+        cur_event = amax + a.starts[nb - 1];
+        if (lane == 0) a.read_tb[nb] = cur_event + 1;
+        st = tb2_tb_seg_abs_ms_dyn(mch, tb_chunk, a.starts, nb, mask_seq_len, bw, thresh, &cur_event,
+                                   a.read_tb);
         if (st != TB2_OK) return st;
     } else {
         // last masked row -> lane-transposed buffer 1 (source and destination disjoint)

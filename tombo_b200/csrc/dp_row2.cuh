@@ -42,7 +42,8 @@ __host__ __device__ __forceinline__ int tb2_abs_chunk(int W) { return tb2_abs_ch
 // packed move words per row and lane
 __host__ __device__ __forceinline__ int tb2_abs_wpr(int ch) { return ch > 16 ? 2 : 1; }
 
-// one speculative walk over the lane's chunk (nothing arrives from the left).  vmask: cells
+// one speculative walk over the lane's chunk (chain input xc: -inf = nothing arrives from
+// the left).  vmask: cells
 // inside the band; skmask: cells that may take a skip (band position 0 may not once the
 // band has moved, _c_dynamic_programming.pyx:261-270, 393-401); tmask (TAIL rows only):
 // cells beyond the signal, whose z-score is the mask fill (:366-372).
@@ -50,13 +51,13 @@ __host__ __device__ __forceinline__ int tb2_abs_wpr(int ch) { return ch > 16 ? 2
 // bit i of `mcd` = that candidate beat the stay (code: mcd ? (msk ? 1 : 2) : 0).
 template <int CH, bool TAIL>
 __device__ __forceinline__ void tb2_abs_walk(const double (&em)[CH], double (&x)[CH], double (&z)[CH],
-                                             double pm1, double mu, double sd, double inv_sd,
-                                             double zs, double mhz, double stay, double skip,
-                                             double maskval, uint32_t vmask, uint32_t skmask,
-                                             uint32_t tmask, uint32_t &msk, uint32_t &mcd)
+                                             double pm1, double xc, double mu, double sd,
+                                             double inv_sd, double zs, double mhz, double stay,
+                                             double skip, double maskval, uint32_t vmask,
+                                             uint32_t skmask, uint32_t tmask, uint32_t &msk,
+                                             uint32_t &mcd)
 {
     const double NEG = tb2_neg_inf();
-    double xc = NEG;
     uint32_t ms = 0u, mc = 0u;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
@@ -155,10 +156,10 @@ __device__ __noinline__ int tb2_adaptive_rows_abs(const PassCtx &pc, const DpCon
         if (cur_start + W > n_em) {
             // band reaches beyond the signal: those cells take the mask fill
             const int tl = min(max(n_em - e0, 0), CH);
-            tb2_abs_walk<CH, true>(em, x, z, pm1, mu, sd, inv_sd, zs, mhz, stay, skip, maskval, vmask,
+            tb2_abs_walk<CH, true>(em, x, z, pm1, NEG, mu, sd, inv_sd, zs, mhz, stay, skip, maskval, vmask,
                                    skmask, ~((1u << tl) - 1u), msk, mcd);
         } else {
-            tb2_abs_walk<CH, false>(em, x, z, pm1, mu, sd, inv_sd, zs, mhz, stay, skip, maskval, vmask,
+            tb2_abs_walk<CH, false>(em, x, z, pm1, NEG, mu, sd, inv_sd, zs, mhz, stay, skip, maskval, vmask,
                                     skmask, 0u, msk, mcd);
         }
         // ---- fix-up: lanes whose true left input is larger re-walk a prefix.  A larger
@@ -281,6 +282,231 @@ __device__ __noinline__ int tb2_tb_seg_abs(const uint32_t *tb, const int *starts
     *cur_event_io = cur_event;
     __syncwarp();
     return TB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Wide bands (bandwidth 1200, the save bandwidth 1500): NS chunks per lane.  The band
+// spans up to 32*NS chunks; chunk c lives in slot c % (32*NS) = (slab (c/32) % NS, lane
+// c % 32).  A row is NS passes in band order; in a pass the 32 lanes hold 32 consecutive
+// chunks exactly as in the single-chunk engine (state comes from / goes back to the lane's
+// slab in shared memory: [slab][cell][lane], conflict free), and the chain value leaving the
+// pass's last chunk enters the next pass's first chunk exactly -- no speculation between
+// passes.  Shared memory per warp: 2 * NS * CH * 32 doubles (event means + row values).
+// ---------------------------------------------------------------------------
+template <int CH, int NS>
+__device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const DpConsts &c, int r_begin,
+                                                     int r_end, int nb_total, double *st_s,
+                                                     const double *rowbuf, uint32_t *tb, int *argmax_io)
+{
+    constexpr int WPR = (CH > 16) ? 2 : 1;
+    constexpr int NSL = 32 * NS;
+    const int lane = tb2_lane();
+    const int W = pc.W, half_bw = W / 2, n_em = pc.n_em;
+    const double NEG = tb2_neg_inf();
+    const double stay = c.stay_pen, skip = c.skip_pen, zs = c.z_shift;
+    const double mhz = c.winsor ? c.mhz : __longlong_as_double(0x7ff0000000000000LL);
+    const double maskval = pc.mask_fill;
+    const double *em_g = pc.em;
+    const int left_lane = (lane + 31) & 31;
+    double *em_s = st_s + lane, *x_s = st_s + NS * CH * 32 + lane;   // [(slab * CH + i) * 32]
+    int prev_start = pc.starts[r_begin - 1];
+    int last_argmax = *argmax_io;
+    int c_lo_prev = prev_start / CH;
+    {
+        // initial state: fwd row r_begin from the wavefront row buffer, which shares the
+        // shared memory with the slabs -- read everything first, then write
+        double tmp[NS][CH];
+        const int k = (lane - c_lo_prev) & 31;
+#pragma unroll
+        for (int p = 0; p < NS; ++p)
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int j = (c_lo_prev + 32 * p + k) * CH + i - prev_start;
+                tmp[p][i] = ((unsigned)j < (unsigned)W) ? rowbuf[j] : NEG;
+            }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < NS; ++p) {
+            const int ch = c_lo_prev + 32 * p + k, sb = ((ch >> 5) % NS) * CH;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int e = ch * CH + i;
+                x_s[(sb + i) * 32] = tmp[p][i];
+                em_s[(sb + i) * 32] = (e < n_em) ? __ldg(em_g + e) : 0.0;
+            }
+        }
+        __syncwarp();
+    }
+    for (int r = r_begin; r < r_end; ++r) {
+        int cur_start = prev_start + last_argmax - half_bw + 1;          // :344-358
+        if (cur_start < prev_start) cur_start = prev_start;
+        if (cur_start >= n_em) {
+            if (r < nb_total - 2) return TB2_ERR_ADAPTIVE_BEYOND_SIGNAL;
+            cur_start = n_em - 1;
+        }
+        if (lane == 0) pc.starts[r] = cur_start;
+        const int d = cur_start - prev_start;
+        const double mu = __ldg(pc.rm + r), sd = __ldg(pc.rs_ + r);
+        const double inv_sd = __drcp_rn(sd);
+        const int c_lo = cur_start / CH;
+        const int k = (lane - c_lo) & 31;                  // position of this lane in a pass
+        const int last_lane = (c_lo + 31) & 31;            // lane holding a pass's last chunk
+        const bool tail = cur_start + W > n_em;
+        // previous-row cell left of the band's first chunk (diagonal source of its cell 0):
+        // still in its slot if that chunk was in the previous row's window, else outside
+        double carry_pm1 = NEG;
+        if (c_lo > c_lo_prev) {
+            const int cp = c_lo - 1;
+            carry_pm1 = st_s[NS * CH * 32 + ((((cp >> 5) % NS) * CH + CH - 1) * 32) + (cp & 31)];
+        }
+        double carry_x = NEG;
+        double lbest = NEG;
+        int lbest_e = 0x7fffffff;
+#pragma unroll
+        for (int p = 0; p < NS; ++p) {
+            const int ch = c_lo + 32 * p + k, sb = ((ch >> 5) % NS) * CH, e0 = ch * CH;
+            const bool is_new = ch >= c_lo_prev + NSL;     // entered the window with this row
+            double em[CH], x[CH], z[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                if (is_new) {
+                    x[i] = NEG;
+                    em[i] = (e0 + i < n_em) ? __ldg(em_g + e0 + i) : 0.0;
+                    em_s[(sb + i) * 32] = em[i];
+                } else {
+                    x[i] = x_s[(sb + i) * 32];
+                    em[i] = em_s[(sb + i) * 32];
+                }
+            }
+            double pm1 = __shfl_sync(TB2_FULL_MASK, x[CH - 1], left_lane);
+            const double next_pm1 = __shfl_sync(TB2_FULL_MASK, x[CH - 1], last_lane);
+            const bool head = k == 0;                      // first chunk of the pass: exact inputs
+            if (head) pm1 = carry_pm1;
+            const int lo = min(max(cur_start - e0, 0), CH);
+            const int hi = min(max(cur_start + W - e0, 0), CH);
+            const uint32_t vmask = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+            const uint32_t skmask = (p == 0 && head && d >= 1) ? (vmask & ~(1u << lo)) : vmask;
+            const double xc0 = head ? carry_x : NEG;
+            uint32_t msk, mcd;
+            if (tail) {
+                const int tl = min(max(n_em - e0, 0), CH);
+                tb2_abs_walk<CH, true>(em, x, z, pm1, xc0, mu, sd, inv_sd, zs, mhz, stay, skip, maskval,
+                                       vmask, skmask, ~((1u << tl) - 1u), msk, mcd);
+            } else {
+                tb2_abs_walk<CH, false>(em, x, z, pm1, xc0, mu, sd, inv_sd, zs, mhz, stay, skip, maskval,
+                                        vmask, skmask, 0u, msk, mcd);
+            }
+            double x_end = x[CH - 1], last_in = NEG;
+            for (;;) {
+                const double xin = __shfl_sync(TB2_FULL_MASK, x_end, left_lane);
+                const bool need = !head && (xin > last_in);
+                if (!__any_sync(TB2_FULL_MASK, need)) break;
+                bool run = need;
+                double xx = xin;
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    run = run && ((vmask >> i) & 1u);
+                    const double a = (xx - stay) + z[i];
+                    const double old = x[i];
+                    run = run && (a >= old);
+                    if (run) { x[i] = a; mcd &= ~(1u << i); }
+                    xx = a;
+                }
+                x_end = x[CH - 1];
+                if (need) last_in = xin;
+            }
+#pragma unroll
+            for (int i = 0; i < CH; ++i) x_s[(sb + i) * 32] = x[i];
+            carry_x = __shfl_sync(TB2_FULL_MASK, x_end, last_lane);
+            carry_pm1 = next_pm1;
+            uint32_t *trow = tb + ((size_t)(r - r_begin) * NS + p) * WPR * 32 + lane;
+            if (WPR == 1) trow[0] = msk | (mcd << 16);
+            else { trow[0] = msk; trow[32] = mcd; }
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                if (x[i] > lbest) { lbest = x[i]; lbest_e = e0 + i; }
+        }
+        // first arg-max of the row: warp maximum, then the smallest event holding it
+        double wbest = lbest;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_xor_sync(TB2_FULL_MASK, wbest, off);
+            wbest = (ob > wbest) ? ob : wbest;
+        }
+        const int win_e = __reduce_min_sync(TB2_FULL_MASK, (lbest == wbest) ? lbest_e : 0x7fffffff);
+        last_argmax = win_e - cur_start;
+        if (last_argmax < 0 || last_argmax >= W) last_argmax = 0;
+        prev_start = cur_start;
+        c_lo_prev = c_lo;
+        __syncwarp();
+    }
+    *argmax_io = last_argmax;
+    return TB2_OK;
+}
+
+template <int CH, int NS>
+__device__ __noinline__ int tb2_tb_seg_abs_ms(const uint32_t *tb, const int *starts, int row_hi, int row_lo,
+                                              int W, int thresh, int *cur_event_io, int *read_tb)
+{
+    constexpr int WPR = (CH > 16) ? 2 : 1;
+    const int lane = tb2_lane();
+    int cur_event = *cur_event_io;
+    for (int sp = row_hi; sp > row_lo; --sp) {
+        const int row = sp - 1;
+        const int st = starts[row];
+        const int c_lo = st / CH;
+        uint32_t w[NS][WPR];
+#pragma unroll
+        for (int p = 0; p < NS; ++p)
+#pragma unroll
+            for (int q = 0; q < WPR; ++q)
+                w[p][q] = tb[(((size_t)(row - row_lo) * NS + p) * WPR + q) * 32 + lane];
+        int bp = cur_event - st;
+        if (bp < 0 || bp >= W) return TB2_ERR_UNEXPECTED;
+        bool diag;
+        for (;;) {
+            const int e = st + bp;
+            const int ch = e / CH, i = e - ch * CH, p = (ch - c_lo) >> 5;
+            uint32_t a = w[0][0], b = w[0][WPR - 1];
+#pragma unroll
+            for (int q = 1; q < NS; ++q) if (p == q) { a = w[q][0]; b = w[q][WPR - 1]; }
+            const uint32_t ms = __shfl_sync(TB2_FULL_MASK, a, ch & 31);
+            uint32_t mc;
+            if (WPR == 2) mc = __shfl_sync(TB2_FULL_MASK, b, ch & 31);
+            else mc = ms >> 16;
+            if ((mc >> i) & 1u) { diag = !((ms >> i) & 1u); break; }
+            --bp;
+            if (bp < 0) return TB2_ERR_UNEXPECTED;
+        }
+        if (diag) --bp;
+        if (thresh >= 0 && min(bp, W - bp - 1) < thresh) return TB2_ERR_BEYOND_BANDWIDTH;
+        cur_event = st + bp;
+        if (lane == 0) read_tb[row] = cur_event + 1;
+    }
+    *cur_event_io = cur_event;
+    __syncwarp();
+    return TB2_OK;
+}
+
+__device__ int tb2_adaptive_rows_abs_ms_dyn(int ch, const PassCtx &pc, const DpConsts &c, int r_begin,
+                                            int r_end, int nb_total, double *st_s, const double *rowbuf,
+                                            uint32_t *tb, int *amax)
+{
+    switch (ch) {
+    case 13: return tb2_adaptive_rows_abs_ms<13, TB2_ABS_MS_SLABS>(pc, c, r_begin, r_end, nb_total, st_s, rowbuf, tb, amax);
+    case 17: return tb2_adaptive_rows_abs_ms<17, TB2_ABS_MS_SLABS>(pc, c, r_begin, r_end, nb_total, st_s, rowbuf, tb, amax);
+    default: return TB2_ERR_CAPACITY;
+    }
+}
+
+__device__ int tb2_tb_seg_abs_ms_dyn(int ch, const uint32_t *tb, const int *starts, int row_hi,
+                                     int row_lo, int W, int thresh, int *cur_event, int *read_tb)
+{
+    switch (ch) {
+    case 13: return tb2_tb_seg_abs_ms<13, TB2_ABS_MS_SLABS>(tb, starts, row_hi, row_lo, W, thresh, cur_event, read_tb);
+    case 17: return tb2_tb_seg_abs_ms<17, TB2_ABS_MS_SLABS>(tb, starts, row_hi, row_lo, W, thresh, cur_event, read_tb);
+    default: return TB2_ERR_CAPACITY;
+    }
 }
 
 __device__ int tb2_adaptive_rows_abs_dyn(int ch, const PassCtx &pc, const DpConsts &c, int r_begin,

@@ -44,6 +44,35 @@ struct AlignLaunchCfg {
 // launches the persistent warp-per-read kernel on ctx->stream
 int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cfg);
 
+// chunk width of the register engine for the adaptive band (dp_row2.cuh), 0 = band too wide
+#if defined(__CUDACC__) || defined(TB2_EMUL)
+__host__ __device__
+#endif
+static inline int tb2_abs_chunk_host(long long W)
+{
+    return W <= 218 ? 7 : (W <= 311 ? 10 : (W <= 404 ? 13 : (W <= 528 ? 17 : 0)));
+}
+// wide bands: three chunks per lane (dp_row2.cuh, multi-slab engine); chunk width or 0
+#if defined(__CUDACC__) || defined(TB2_EMUL)
+__host__ __device__
+#endif
+static inline int tb2_abs_ms_chunk_host(long long W)
+{
+    return (W > 528 && W <= 95 * 13 + 1) ? 13 : ((W > 528 && W <= 95 * 17 + 1) ? 17 : 0);
+}
+#define TB2_ABS_MS_SLABS 3
+// packed-move words per adaptive row and lane for band width W (register engines), 0 if the
+// band runs on the lane-chunk engine
+#if defined(__CUDACC__) || defined(TB2_EMUL)
+__host__ __device__
+#endif
+static inline int tb2_abs_words_per_row(long long W)
+{
+    const int c1 = tb2_abs_chunk_host(W);
+    if (c1) return c1 > 16 ? 2 : 1;
+    const int c3 = tb2_abs_ms_chunk_host(W);
+    return c3 ? TB2_ABS_MS_SLABS * (c3 > 16 ? 2 : 1) : 0;
+}
 // capacity helper (host): packed-move words needed for (rows, W)
 #define TB2_MAX_CHUNK 256   // cells per lane: band widths up to 8192 (dp_align.cuh)
 // wavefront engine: step-space move words, 32 * (strip span / 16 + 1) per 32-row strip
@@ -58,16 +87,9 @@ static inline size_t tb2_tb_words(long long rows, long long W, long long drift)
     long long chunk = (W + 31) / 32;
     long long wpl = (chunk + 15) / 16;
     wpl = wpl <= 5 ? wpl : (wpl <= 8 ? 8 : 16);   // instantiated widths (tb2_wpl_of)
+    if (tb2_abs_words_per_row(W) > wpl) wpl = tb2_abs_words_per_row(W);
     // lane-chunk rows (wpl * 32 words) plus wavefront rows: an upper bound valid for
     // every mix of the two engines
     return (size_t)(rows * wpl * 32) + tb2_wf_words_bound(rows, W, drift);
-}
-// chunk width of the register engine for the adaptive band (dp_row2.cuh), 0 = band too wide
-#if defined(__CUDACC__) || defined(TB2_EMUL)
-__host__ __device__
-#endif
-static inline int tb2_abs_chunk_host(long long W)
-{
-    return W <= 218 ? 7 : (W <= 311 ? 10 : (W <= 404 ? 13 : (W <= 528 ? 17 : 0)));
 }
 static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }

@@ -185,9 +185,11 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
             // start rows need one plain row; wider bands keep two (four up to 512) transposed
             // rows for the lane-chunk engine
             const long long bw_cells = tb2_row_cells(p.bandwidth);
-            const long long bw_pairs = tb2_abs_chunk_host(p.bandwidth) != 0
-                                           ? (p.bandwidth + 1) / 2
-                                           : (p.bandwidth <= 512 ? 2 * bw_cells : bw_cells);
+            const long long bw_pairs =
+                tb2_abs_chunk_host(p.bandwidth) != 0 ? (p.bandwidth + 1) / 2
+                : tb2_abs_ms_chunk_host(p.bandwidth) != 0
+                    ? (long long)TB2_ABS_MS_SLABS * tb2_abs_ms_chunk_host(p.bandwidth) * 32
+                    : (p.bandwidth <= 512 ? 2 * bw_cells : bw_cells);
             cl->smem_cells = std::max(cl->smem_cells,
                                       tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2, bw_pairs)));
             cl->tb_words = std::max(cl->tb_words, std::max(tb2_tb_words(nb, p.bandwidth, n_em + p.bandwidth),
