@@ -1142,13 +1142,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                         const unsigned int slot = atomicAdd(&t.nbuf, 1u);
                         if (slot < QCAP) queue[slot] = ((unsigned int)i << 16) | (unsigned int)j;
                     };
-                    // fp32 images of ev that coincide (the reference's slope is then 1000.0) are
-                    // adjacent after the sort; a read without any takes the loops below without
-                    // the per-pair equality test (0.2 % of reads have one)
                     {
-                        int tie = 0;
-                        for (int i = tid; i + 1 < n; i += ST_THREADS) tie |= (t.pt[i].z == t.pt[i + 1].z);
-                        tie = __syncthreads_or(tie);
                         // thread c owns columns ja = c and jb = n - 1 - c (ja <= jb): rows
                         // i < ja are tested against both with one load of point i
                         const int half = (n + 1) / 2;
@@ -1158,51 +1152,6 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                             const float xla = pa.x + gLf, yha = pa.y - gHf;
                             const float xlb = pb.x + gLf, yhb = pb.y - gHf;
                             int i = 0;
-                            if (!tie) {
-                                // blocks of 32 rows: decided pairs are settled in registers, the
-                                // undecided ones only set a bit; the bits are queued after the
-                                // block, so the hot loop has no divergent branch
-                                if (ja != jb) {
-                                    for (; i + 32 <= ja; i += 32) {
-                                        uint32_t ua = 0u, ub = 0u;
-#pragma unroll
-                                        for (int k = 0; k < 32; ++k) {
-                                            const float4 pi = t.pt[i + k];
-                                            const bool la = pi.x > xla, ha = pi.y < yha;
-                                            const bool lb = pi.x > xlb, hb = pi.y < yhb;
-                                            below += la; below += lb;
-                                            if (!(la || ha)) ua |= 1u << k;
-                                            if (!(lb || hb)) ub |= 1u << k;
-                                        }
-                                        while (ua) { const int k = __ffs((int)ua) - 1; ua &= ua - 1u; push(i + k, ja); }
-                                        while (ub) { const int k = __ffs((int)ub) - 1; ub &= ub - 1u; push(i + k, jb); }
-                                    }
-                                    for (; i < ja; ++i) {
-                                        const float4 pi = t.pt[i];
-                                        const bool la = pi.x > xla, ha = pi.y < yha;
-                                        const bool lb = pi.x > xlb, hb = pi.y < yhb;
-                                        if (la || ha) below += la; else push(i, ja);
-                                        if (lb || hb) below += lb; else push(i, jb);
-                                    }
-                                }
-                                for (; i + 32 <= jb; i += 32) {
-                                    uint32_t ub = 0u;
-#pragma unroll
-                                    for (int k = 0; k < 32; ++k) {
-                                        const float4 pi = t.pt[i + k];
-                                        const bool lb = pi.x > xlb, hb = pi.y < yhb;
-                                        below += lb;
-                                        if (!(lb || hb)) ub |= 1u << k;
-                                    }
-                                    while (ub) { const int k = __ffs((int)ub) - 1; ub &= ub - 1u; push(i + k, jb); }
-                                }
-                                for (; i < jb; ++i) {
-                                    const float4 pi = t.pt[i];
-                                    const bool lb = pi.x > xlb, hb = pi.y < yhb;
-                                    if (lb || hb) below += lb; else push(i, jb);
-                                }
-                                continue;
-                            }
                             if (ja != jb) {
 #pragma unroll 4
                                 for (; i < ja; ++i) {
