@@ -145,6 +145,24 @@ inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 inline void __syncwarp(unsigned m = 0xffffffffu) { emul::check_mask(m); emul::xchg(0, 0); }
 inline void __syncthreads() { emul::block_barrier(); }
+namespace emul {
+// block-wide reductions of a predicate (two barriers: deposit, read)
+inline int block_reduce(int v, int mode)
+{
+    static std::vector<int> slots;
+    Block *blk = B;
+    if (slots.size() < blk->f.size()) slots.resize(blk->f.size());
+    slots[me().tid] = v;
+    block_barrier();
+    int orv = 0, andv = 1, cnt = 0;
+    for (size_t i = 0; i < blk->f.size(); ++i) { orv |= slots[i] != 0; andv &= slots[i] != 0; cnt += slots[i] != 0; }
+    block_barrier();
+    return mode == 0 ? orv : (mode == 1 ? andv : cnt);
+}
+}
+inline int __syncthreads_or(int p) { return emul::block_reduce(p, 0); }
+inline int __syncthreads_and(int p) { return emul::block_reduce(p, 1); }
+inline int __syncthreads_count(int p) { return emul::block_reduce(p, 2); }
 inline int __reduce_add_sync(unsigned m, int v)
 {
     emul::check_mask(m);
@@ -170,6 +188,33 @@ inline unsigned __reduce_and_sync(unsigned m, unsigned v)
     emul::xchg(v, 0, all);
     unsigned s = 0xffffffffu;
     for (int i = 0; i < 32; ++i) s &= (unsigned)all[i];
+    return s;
+}
+inline unsigned __reduce_max_sync(unsigned m, unsigned v)
+{
+    emul::check_mask(m);
+    uint64_t all[32];
+    emul::xchg((uint64_t)v, 0, all);
+    unsigned s = (unsigned)all[0];
+    for (int i = 1; i < 32; ++i) s = s > (unsigned)all[i] ? s : (unsigned)all[i];
+    return s;
+}
+inline unsigned __reduce_min_sync(unsigned m, unsigned v)
+{
+    emul::check_mask(m);
+    uint64_t all[32];
+    emul::xchg((uint64_t)v, 0, all);
+    unsigned s = (unsigned)all[0];
+    for (int i = 1; i < 32; ++i) s = s < (unsigned)all[i] ? s : (unsigned)all[i];
+    return s;
+}
+inline unsigned __reduce_add_sync(unsigned m, unsigned v)
+{
+    emul::check_mask(m);
+    uint64_t all[32];
+    emul::xchg((uint64_t)v, 0, all);
+    unsigned s = 0;
+    for (int i = 0; i < 32; ++i) s += (unsigned)all[i];
     return s;
 }
 inline int __reduce_max_sync(unsigned m, int v)
@@ -201,6 +246,12 @@ inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return sqrt(a); }
 inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __fdividef(float a, float b) { return a / b; }
+struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+using std::isfinite;
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }

@@ -109,3 +109,53 @@ def align_batch(reads, params, sig_match_thresh=1.1, klass=0, n_blocks=1, smem_c
                         starts=starts[bo:bo + nb].copy(),
                         read_tb=read_tb[bo + i:bo + i + nb + 1].copy()))
     return out
+
+
+# ---------------------------------------------------------------- stage kernels
+_LIB_STAGE = None
+
+
+def stage_lib():
+    global _LIB_STAGE
+    if _LIB_STAGE is None:
+        so = os.path.join(HERE, 'libemul_stage.so')
+        srcs = [os.path.join(HERE, f) for f in ('emul_stage.cpp', 'cuda_emul.cpp', 'cuda_emul.h')]
+        srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(['g++', '-O1', '-g', '-std=c++17', '-ffp-contract=off', '-fPIC',
+                                   '-shared', '-o', so, os.path.join(HERE, 'emul_stage.cpp'),
+                                   os.path.join(HERE, 'cuda_emul.cpp')])
+        _LIB_STAGE = C.CDLL(so)
+    return _LIB_STAGE
+
+
+def resolve(segs_dp, rm, rs, norm, params, max_raw_cpts=200, cap_doubles=1 << 15,
+            big_cap_doubles=1 << 22):
+    """k_resolve on one read -> (status, segs)"""
+    from tombo_b200 import _lib
+    L = stage_lib()
+    segs_dp = np.ascontiguousarray(segs_dp, dtype=np.int32)
+    rm, rs, norm = (np.ascontiguousarray(a, dtype=np.float64) for a in (rm, rs, norm))
+    nb = rm.shape[0]
+    out = np.zeros(nb + 1, dtype=np.int32)
+    st = C.c_int(0)
+    ps = _lib.params_struct(params)
+    L.emul_resolve(segs_dp.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(nb),
+                   rm.ctypes.data_as(C.POINTER(C.c_double)), rs.ctypes.data_as(C.POINTER(C.c_double)),
+                   norm.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(norm.shape[0]), C.byref(ps),
+                   C.c_longlong(-1 if max_raw_cpts is None else max_raw_cpts),
+                   C.c_longlong(cap_doubles), C.c_longlong(big_cap_doubles),
+                   out.ctypes.data_as(C.POINTER(C.c_int)), C.byref(st))
+    return st.value, out.astype(np.int64)
+
+
+def theil_sen(prev_shift, prev_scale, bm, rm, key=0):
+    """k_theil_sen on one read -> (status, (shift, scale, shift_corr, scale_corr))"""
+    L = stage_lib()
+    bm, rm = (np.ascontiguousarray(a, dtype=np.float64) for a in (bm, rm))
+    out = np.zeros(4)
+    st = C.c_int(0)
+    L.emul_theil_sen(bm.ctypes.data_as(C.POINTER(C.c_double)), rm.ctypes.data_as(C.POINTER(C.c_double)),
+                     C.c_int(bm.shape[0]), C.c_double(prev_shift), C.c_double(prev_scale),
+                     C.c_uint(key), out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st))
+    return st.value, tuple(out.tolist())

@@ -1,0 +1,73 @@
+"""CPU: stage kernels' device source (tombo_b200/csrc/stage_kernels.cuh) on the host emulation
+of tests/emul, bit-compared with the oracle: skipped-base raw DP (32-row wavefront for DNA,
+serial recurrence for RNA, overflow arena) and Theil-Sen.  An algorithm check of the kernel
+source; the GPU parity tests remain the proof for the compiled kernels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emul'))
+from test_emul_dp_cpu import _events  # noqa: E402
+
+ALN = (4.2, 4.2, 200, 1500, 20.0, 40, 750, 2500, 250)
+
+
+def _dp_segs(orc, kmer_ref, cpos, rp, nb, seed, stall=None, kind='DNA'):
+    from tombo_b200 import synthetic as syn
+    means, sds = syn.kmer_table(kmer_ref)
+    r = syn.make_read(kmer_ref, cpos, nb, seed, stall=stall, kind=kind)
+    cp, em, rm, rs = _events(orc, r, means, sds, rp, k=len(kmer_ref[0][0]))
+    st, norm, sv = orc.normalize_raw_signal(np.asarray(r.raw, dtype=np.float64), 5.0)
+    st, segs, rsrtr, dbg, epb = orc.find_adaptive_base_assignment(cp, em, rp, rm, rs)
+    assert st == 0
+    return segs, rm, rs, norm[rsrtr:rsrtr + segs[-1]], sv
+
+
+@pytest.mark.parametrize('nb,seed,stall,raw_min_obs,cap', [
+    (444, 9000, None, 1, 1 << 15), (300, 9001, None, 1, 1 << 15),
+    (600, 9002, (300, 1500), 1, 1 << 15),          # a stall: 78 skipped bases, big windows
+    (800, 9004, (400, 3000), 1, 4096),             # windows beyond the slab: overflow arena
+    (444, 9005, None, 2, 1 << 15),                 # raw_min_obs_per_base 2: serial recurrence
+    (600, 9006, (300, 1500), 2, 1 << 15),
+])
+def test_resolve_skipped_bases_matches_oracle(orc, dna_model, RPcls, nb, seed, stall, raw_min_obs, cap):
+    import emul
+    kmer_ref, cpos = dna_model
+    rp = RPcls(ALN, (5, 3, raw_min_obs, 5))
+    segs, rm, rs, nsig, sv = _dp_segs(orc, kmer_ref, cpos, rp, nb, seed, stall)
+    so, oseg = orc.resolve_skipped_bases_with_raw(segs, rm, rs, nsig, rp)
+    se, eseg = emul.resolve(segs, rm, rs, nsig, rp, cap_doubles=cap)
+    assert se == so
+    if so == 0:
+        assert np.array_equal(eseg, oseg)
+
+
+def test_resolve_failure_statuses_and_capacity(orc, dna_model, RPcls):
+    import emul
+    kmer_ref, cpos = dna_model
+    rp = RPcls(ALN)
+    segs, rm, rs, nsig, sv = _dp_segs(orc, kmer_ref, cpos, rp, 800, 9004, (400, 3000))
+    # too many deletions in one window (max_raw_cpts): the reference's message, same status
+    so, _ = orc.resolve_skipped_bases_with_raw(segs, rm, rs, nsig, rp, max_raw_cpts=20)
+    se, _ = emul.resolve(segs, rm, rs, nsig, rp, max_raw_cpts=20)
+    assert so == se == 5
+    # slab and arena both too small: a loud capacity failure, never a different answer
+    se, _ = emul.resolve(segs, rm, rs, nsig, rp, cap_doubles=1024, big_cap_doubles=1024)
+    assert se == 202
+
+
+@pytest.mark.parametrize('nb,seed', [(444, 9100), (61, 9101), (999, 9102), (1400, 9103)])
+def test_theil_sen_matches_oracle(orc, dna_model, RPcls, nb, seed):
+    """> 1000 bases: keyed sub-sampling, identical on both sides"""
+    import emul
+    kmer_ref, cpos = dna_model
+    rp = RPcls((4.2, 4.2, 400, 1500, 20.0, 40, 750, 2500, 250))
+    segs, rm, rs, nsig, sv = _dp_segs(orc, kmer_ref, cpos, rp, nb, seed)
+    st, seg2 = orc.resolve_skipped_bases_with_raw(segs, rm, rs, nsig, rp)
+    assert st == 0
+    bm = orc.new_means(nsig, seg2)
+    s1, o1 = orc.theil_sen(sv[0], sv[1], bm, rm, key=77)
+    s2, o2 = emul.theil_sen(sv[0], sv[1], bm, rm, key=77)
+    assert s1 == s2 and o1[:2] == o2[:2]

@@ -1,6 +1,12 @@
 // batch.h -- device-resident layout of one batch of reads (host + device view)
 #pragma once
+#ifdef TB2_EMUL   // host emulation of the device code (tests/emul): no CUDA runtime types
+#include <stddef.h>
+#include "../../include/tombo_b200.h"
+struct tb2_ctx;
+#else
 #include "ctx.h"
+#endif
 
 // Per-read state.  One resquiggle_read "call" (resquiggle.py:1122-1214) is one
 // trip through the stage kernels; the worker policy (resquiggle.py:1492-1504,

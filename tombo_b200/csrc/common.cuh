@@ -14,6 +14,13 @@
 
 #define TB2_FULL_MASK 0xffffffffu
 
+// dynamic shared memory of a kernel (tests/emul substitutes its arena)
+#ifdef TB2_EMUL
+#define TB2_DYN_SMEM(T, name) T *name = (T *)emul::B->smem
+#else
+#define TB2_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 __device__ __forceinline__ double tb2_neg_inf()
 {
     return __longlong_as_double((long long)0xfff0000000000000ULL);

@@ -4,12 +4,6 @@
 #include "dp_align.cuh"
 #include "kernels.h"
 
-#ifdef TB2_EMUL
-#define TB2_DYN_SMEM(T, name) T *name = (T *)emul::B->smem
-#else
-#define TB2_DYN_SMEM(T, name) extern __shared__ T name[]
-#endif
-
 #define ALIGN_WARPS 4
 
 // ---------------------------------------------------------------------------

@@ -114,8 +114,12 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
                 // warp-aggregated: the leading digits of real signals are almost all
                 // equal, one atomic per distinct digit instead of one per lane
                 const unsigned int dg = (unsigned int)(key >> shift) & 255u;
+#ifdef TB2_EMUL   // the host emulation has full-mask collectives only; same histogram
+                atomicAdd(&sm.hist[dg], 1u);
+#else
                 const unsigned int peers = __match_any_sync(__activemask(), dg);
                 if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&sm.hist[dg], __popc(peers));
+#endif
             }
         }
         __syncthreads();
