@@ -71,3 +71,33 @@ def test_theil_sen_matches_oracle(orc, dna_model, RPcls, nb, seed):
     s1, o1 = orc.theil_sen(sv[0], sv[1], bm, rm, key=77)
     s2, o2 = emul.theil_sen(sv[0], sv[1], bm, rm, key=77)
     assert s1 == s2 and o1[:2] == o2[:2]
+
+
+def test_theil_sen_adversarial_inputs_match_oracle(orc):
+    """quantised values (ties, collinear triples), clipped plateaus (equal ev), heavy tails,
+    nearly collinear points: whichever path the kernel takes, the doubles are the oracle's"""
+    import emul
+    rs = np.random.RandomState(1)
+    for it in range(36):
+        n = int(rs.choice([128, 129, 200, 257, 444, 511, 512, 513, 700, 1000]))
+        kind = it % 6
+        ev = rs.normal(0, 1.5, n)
+        if kind == 0:
+            md = ev * 1.03 + 0.05 + rs.normal(0, 0.1, n)
+        elif kind == 1:
+            md = ev * 0.9 + rs.standard_cauchy(n) * 0.05
+        elif kind == 2:
+            ev = np.round(ev * 64) / 64
+            md = np.round((ev * 1.1 + rs.normal(0, 0.2, n)) * 64) / 64
+        elif kind == 3:
+            md = rs.normal(0, 1, n)
+        elif kind == 4:
+            ev = np.clip(ev, -2.0, 2.0)
+            md = ev + rs.normal(0, 0.05, n)
+        else:
+            md = ev * 1.0 + rs.normal(0, 1e-9, n)
+        s1, o1 = orc.theil_sen(0.3, 1.7, ev, md, key=9)
+        s2, o2 = emul.theil_sen(0.3, 1.7, ev, md, key=9)
+        assert s1 == s2, (it, n, kind)
+        if s1 == 0:
+            assert o1[:2] == o2[:2], (it, n, kind)

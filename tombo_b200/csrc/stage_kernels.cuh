@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_base_means(BatchView b)
 // bin, whose members are selected exactly (generic radix select as fall-back).
 // ===========================================================================
 // debug counters (tests / tuning): [0] Theil-Sen reads, [1] fast path, [2] exact
-// histogram path, [3] generic select path
+// histogram path, [3] generic select path, [5] sort-and-sweep path, [6] ... abandoned
 __device__ unsigned long long g_tb2_counters[8];
 
 #define TS_MAX 1000
@@ -997,6 +997,111 @@ __device__ __forceinline__ void ts_pair_of(long long s, int n, int *pi, int *pj)
     while (row_start(i + 1) <= s) ++i;
     *pi = i;
     *pj = (int)(s - row_start(i)) + i + 1;
+}
+
+
+// ---------------------------------------------------------------------------
+// Sort-and-sweep median of the pairwise slopes (round 2).  With the points sorted by ev,
+// a pair a < b has slope < T  <=>  Q_T(a) > Q_T(b),  Q_T(k) = md_k - T * ev_k: the number
+// of slopes below T is the inversion count of the sequence Q_T, and the pairs whose slope
+// lies in [T1, T2) are exactly the adjacent transpositions that turn the Q_T1 order into
+// the Q_T2 order.  So instead of testing all n(n-1)/2 pairs against a bracket:
+//   1. a 2048-pair sample histogram places three thresholds L < H1 < H2 below / around the
+//      median ranks (cheap; only has to be roughly right);
+//   2. one merge sort by Q_L counts the slopes below L exactly (O(n log^2 n));
+//   3. odd-even transposition passes re-sort to Q_H1 (counting swaps) and then to Q_H2
+//      (listing the swapped pairs): a few dozen passes, since few pairs cross;
+//   4. the listed pairs (~1 % of all) get the reference's exact fp64 quotient and one
+//      radix select returns the order statistics np.median sees.
+// Exactness: every comparison is made on fp64 Q values; after each (re)sort all adjacent
+// gaps must exceed a guard g = 1e-12 * M * (1 + |T|) -- then NO pair is within g of the
+// threshold, the computed order is the real-arithmetic order, and the reference's rounded
+// quotient (within 3 ulp of the real slope) falls on the same side.  Any doubt (a gap within
+// the guard, equal ev, thresholds that miss the median ranks, an overflowing list) abandons
+// this path for the exhaustive one below -- never a different answer.
+// ---------------------------------------------------------------------------
+#define TS_SBINS 1024          // bins of the sample histogram over [lo, hi)
+#define TS_SAMPLES 2048
+#define TS_LIST 2048           // listed (swapped) pairs, u32 each
+#define TS_MAX_PHASES 600
+
+// stable merge sort of (key, id) by key ascending, ids are positions 0..P-1 in ev order; returns
+// the number of inversions (pairs of positions a < b with key[a] > key[b]).  P is a power of
+// two >= n, keys beyond n are +inf.  On return the sorted arrays are in (*ka, *pa).
+__device__ long long ts_sort_count(double **ka, double **kb, unsigned short **pa, unsigned short **pb,
+                                   int P, SelectSmem &sm)
+{
+    const int tid = threadIdx.x;
+    unsigned int inv = 0;
+    for (int w = 1; w < P; w <<= 1) {
+        const double *src = *ka; const unsigned short *sp = *pa;
+        double *dst = *kb; unsigned short *dp = *pb;
+        for (int p = tid; p < P; p += ST_THREADS) {
+            const int base = p & ~(2 * w - 1), mid = base + w;
+            const double key = src[p];
+            int lo, hi;
+            if (p < mid) {                       // left run: count right elements < key
+                lo = mid; hi = mid + w;
+                while (lo < hi) { const int m = (lo + hi) >> 1; if (src[m] < key) lo = m + 1; else hi = m; }
+                dst[p + (lo - mid)] = key; dp[p + (lo - mid)] = sp[p];
+            } else {                             // right run: count left elements <= key
+                lo = base; hi = mid;
+                while (lo < hi) { const int m = (lo + hi) >> 1; if (src[m] <= key) lo = m + 1; else hi = m; }
+                const int le = lo - base;
+                dst[base + (p - mid) + le] = key; dp[base + (p - mid) + le] = sp[p];
+                inv += (unsigned int)(w - le);   // left elements > key
+            }
+        }
+        __syncthreads();
+        double *tk = *ka; *ka = *kb; *kb = tk;
+        unsigned short *tp = *pa; *pa = *pb; *pb = tp;
+    }
+    // block-wide sum in 64 bits (n <= 1000: < 5e5 inversions, a 32-bit sum is safe)
+    return (long long)tb2_block_sum(inv, sm);
+}
+
+// odd-even transposition re-sort of `perm` (positions -> element ids) by q[] ascending.
+// Returns the number of swaps (pairs that crossed) or -1 if it did not settle; swapped pairs
+// are appended to list[*n_list] as (min id << 16 | max id) when list != nullptr.
+__device__ long long ts_sweep(unsigned short *perm, const double *q, int n, unsigned int *list,
+                              unsigned int *n_list, SelectSmem &sm)
+{
+    const int tid = threadIdx.x;
+    unsigned int swaps = 0;
+    int quiet = 0;
+    for (int ph = 0; ph < TS_MAX_PHASES; ++ph) {
+        int any = 0;
+        for (int p = 2 * tid + (ph & 1); p + 1 < n; p += 2 * ST_THREADS) {
+            const unsigned short x = perm[p], y = perm[p + 1];
+            if (q[x] > q[y]) {
+                perm[p] = y; perm[p + 1] = x;
+                ++swaps; any = 1;
+                if (list) {
+                    const unsigned int slot = atomicAdd(n_list, 1u);
+                    if (slot < TS_LIST) list[slot] = ((unsigned int)min(x, y) << 16) | (unsigned int)max(x, y);
+                }
+            }
+        }
+        any = __syncthreads_or(any);
+        quiet = any ? 0 : quiet + 1;
+        if (quiet >= 2) {
+#ifdef TS_DEBUG
+            if (tid == 0) atomicAdd(&g_tb2_counters[7], (unsigned long long)(ph + 1));
+#endif
+            return (long long)tb2_block_sum(swaps, sm);
+        }
+    }
+    tb2_block_sum(swaps, sm);
+    return -1;
+}
+
+// all adjacent gaps of the order `perm` by q exceed the guard (then no pair at all is within it)
+__device__ bool ts_gaps_ok(const unsigned short *perm, const double *q, int n, double g)
+{
+    int bad = 0;
+    for (int p = threadIdx.x; p + 1 < n; p += ST_THREADS)
+        bad |= !(q[perm[p + 1]] - q[perm[p]] > g);
+    return !__syncthreads_or(bad);
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 4)
@@ -1071,12 +1176,190 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             }
         }
     }
+    // ---- sort-and-sweep path (see the comment above ts_sort_count) ----
+    if (hs >= 16 && n >= 128 && hi > lo) {
+        // shared-memory plan: pt (16 KB) = two key arrays for the merge sort, afterwards the
+        // per-element Q (qa) and the pair list (qb), finally the exact slopes; the hist/buf
+        // union = sample CDF (4.1 KB) followed by the two id arrays (4 KB)
+        double *qa = reinterpret_cast<double *>(t.pt), *qb = qa + TS_PAD;
+        unsigned short *pa = reinterpret_cast<unsigned short *>(t.hist + TS_SBINS + 64), *pb = pa + TS_PAD;
+        unsigned int *list = reinterpret_cast<unsigned int *>(qb);
+        bool ok;
+        double M;
+        // sample size: about one sample per 24 pairs, 2048 .. 8192
+        const int n_samples = (int)min(8192LL, max(2048LL, Np / 24));
+        {
+            // strictly increasing, finite ev (equal ev: the reference's slope is 1000.0 -- other path)
+            int bad = 0;
+            double mx = 0.0;
+            for (int i = tid; i < n; i += ST_THREADS) {
+                const double e = t.ev[i], m = t.md[i];
+                if (!(fabs(e) < 1e300) || !(fabs(m) < 1e300)) bad = 1;
+                if (i + 1 < n && !(t.ev[i + 1] > e)) bad = 1;
+                mx = fmax(mx, fmax(fabs(e), fabs(m)));
+            }
+            ok = !__syncthreads_or(bad);
+#ifdef TS_DEBUG
+            if (!ok && tid == 0) { int c = 0; for (int i = 0; i + 1 < n; ++i) if (!(t.ev[i + 1] > t.ev[i])) { if (c++ < 3) printf("  ev order: i=%d %.17g %.17g\n", i, t.ev[i], t.ev[i + 1]); } }
+#endif
+            unsigned long long mk = (unsigned long long)__double_as_longlong(mx);   // mx >= 0: bit order
+            mk = ~tb2_block_min_u64(~mk, sm);
+            M = fmax(1.0, __longlong_as_double((long long)mk));
+        }
+        // 1. sample histogram of approximate slopes over [lo, hi), turned into a CDF table
+        const float lo_f = (float)lo, hi_f = (float)hi;
+        const float w_f = (hi_f - lo_f) / (float)TS_SBINS;
+        ok = ok && (w_f > 0.0f) && isfinite(w_f);
+        if (ok) {
+            for (int i = tid; i < TS_SBINS + 2; i += ST_THREADS) t.hist[i] = 0;
+            __syncthreads();
+            const float inv_w = 1.0f / w_f;
+            for (int q = tid; q < n_samples; q += ST_THREADS) {
+                const int i = q % n;
+                const int off = 1 + (int)(tb2_mix32((uint32_t)q * 2654435761u + 17u) % (uint32_t)(n - 1));
+                const int j = (i + off) % n;
+                const float sa = __fdividef((float)(t.md[i] - t.md[j]), (float)(t.ev[i] - t.ev[j]));
+                int bin = 0;                                 // bin 0: below lo
+                if (sa >= hi_f) bin = TS_SBINS + 1;          // last: at or above hi (nan lands in bin 0)
+                else if (sa >= lo_f) bin = min(TS_SBINS - 1, (int)((sa - lo_f) * inv_w)) + 1;
+                atomicAdd(&t.hist[bin], 1u);
+            }
+            __syncthreads();
+            const int per = (TS_SBINS + 2 + ST_THREADS - 1) / ST_THREADS;
+            const int q0 = min(TS_SBINS + 2, tid * per), q1 = min(TS_SBINS + 2, q0 + per);
+            unsigned int mine = 0;
+            for (int q = q0; q < q1; ++q) mine += t.hist[q];
+            const int lane = tid & 31, warp = tid >> 5;
+            unsigned int inc = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int o = __shfl_up_sync(TB2_FULL_MASK, inc, off);
+                if (lane >= off) inc += o;
+            }
+            if (lane == 31) sm.warp_tot[warp] = inc;
+            __syncthreads();
+            unsigned int run = inc - mine;
+            for (int q = 0; q < warp; ++q) run += sm.warp_tot[q];
+            for (int q = q0; q < q1; ++q) { run += t.hist[q]; t.hist[q] = run; }   // cum[q]: samples in bins <= q
+            __syncthreads();
+        }
+        // threshold = upper edge of the first bin b (1..TS_SBINS) with cum[b] >= frac * samples
+        auto pick = [&](double frac, int *bsel) -> bool {
+            const double tf = frac * (double)n_samples;
+            if (!(tf > (double)t.hist[0]) || !(tf < (double)t.hist[TS_SBINS])) return false;
+            const unsigned int target = (unsigned int)tf;
+            int blo = 1, bhi = TS_SBINS;
+            while (blo < bhi) { const int m = (blo + bhi) >> 1; if (t.hist[m] >= target) bhi = m; else blo = m + 1; }
+            *bsel = blo;
+            return true;
+        };
+        auto thr = [&](int bsel) { return (double)lo_f + (double)w_f * (double)bsel; };
+        const long long kT = even ? k1 + 1 : k1;
+        const double sig = 0.5 / sqrt((double)n_samples);        // sd of a sample quantile near 0.5
+        const double ppm = (double)Np / (double)n_samples;       // pairs per sample
+        int bL = 0, bH1 = 0, bH2 = 0;
+        long long invL = 0, inv1 = 0, inv2 = 0;
+        if (ok) ok = pick((double)k1 / (double)Np - 4.0 * sig, &bL);
+        if (ok) {
+            // 2. exact count below L: merge sort by Q_L, certainty of the order
+            const double TL = thr(bL);
+            const double gL = 1e-12 * M * (1.0 + fabs(TL));
+            int P = 2;
+            while (P < n) P <<= 1;
+            for (int i = tid; i < P; i += ST_THREADS) {
+                qa[i] = (i < n) ? __fma_rn(-TL, t.ev[i], t.md[i]) : __longlong_as_double(0x7ff0000000000000LL);
+                pa[i] = (unsigned short)i;
+            }
+            __syncthreads();
+            double *ka = qa, *kb = qb;
+            unsigned short *ia = pa, *ib = pb;
+            invL = ts_sort_count(&ka, &kb, &ia, &ib, P, sm);
+            int bad = 0;
+            for (int p2 = tid; p2 + 1 < n; p2 += ST_THREADS) bad |= !(ka[p2 + 1] - ka[p2] > gL);
+            ok = !__syncthreads_or(bad);
+            if (ia != pa) for (int i = tid; i < n; i += ST_THREADS) pa[i] = ia[i];
+            __syncthreads();
+            ok = ok && invL <= k1;
+        }
+        // 3a. approach the median ranks from below with count-only sweeps.  Each exact count
+        // re-calibrates the sample CDF; moving on by D pairs is then predictable to about
+        // sqrt(D * pairs-per-sample), so every stage aims 3 of those sigmas short of rank k1
+        // until the remaining distance fits the pair list
+        bH1 = bL; inv1 = invL;
+        for (int stage = 0; ok && stage < 5; ++stage) {
+            const double D = (double)(k1 - inv1);
+            const double rest = fmax(3.0 * sqrt(D * ppm), 150.0);
+            if (D <= rest + 250.0 || D + 3.0 * sqrt(D * ppm) + 300.0 <= 0.8 * TS_LIST) break;
+            const double delta = (double)inv1 / (double)Np - (double)t.hist[bH1] / (double)n_samples;
+            int bn;
+            if (!pick(((double)k1 - rest) / (double)Np - delta, &bn) || bn <= bH1) break;
+            const double T1 = thr(bn);
+            for (int i = tid; i < n; i += ST_THREADS) qa[i] = __fma_rn(-T1, t.ev[i], t.md[i]);
+            __syncthreads();
+            const long long sw = ts_sweep(pa, qa, n, nullptr, nullptr, sm);
+            ok = sw >= 0 && ts_gaps_ok(pa, qa, n, 1e-12 * M * (1.0 + fabs(T1)));
+            bH1 = bn; inv1 += sw;
+            ok = ok && inv1 <= k1;
+#ifdef TS_DEBUG
+            if (tid == 0) printf("  stage %d: D=%.0f aimed rest %.0f -> got rest %lld (swaps %lld)\n", stage, D, rest, k1 - inv1, sw);
+#endif
+        }
+        if (ok) {
+            // 3b. sweep past the median ranks, listing every pair that crosses
+            const double D = (double)(kT - inv1);
+            const double over = fmax(3.0 * sqrt(fmax(D, 1.0) * ppm), 150.0);
+            const double delta = (double)inv1 / (double)Np - (double)t.hist[bH1] / (double)n_samples;
+            ok = pick(((double)kT + over) / (double)Np - delta, &bH2) && bH2 > bH1;
+            if (ok) {
+                const double T2 = thr(bH2);
+                for (int i = tid; i < n; i += ST_THREADS) qa[i] = __fma_rn(-T2, t.ev[i], t.md[i]);
+                if (tid == 0) t.nbuf = 0;
+                __syncthreads();
+                const long long sw = ts_sweep(pa, qa, n, list, &t.nbuf, sm);
+                ok = sw >= 0 && sw <= TS_LIST && ts_gaps_ok(pa, qa, n, 1e-12 * M * (1.0 + fabs(T2)));
+                inv2 = inv1 + sw;
+                ok = ok && kT < inv2;
+            }
+        }
+        if (ok) {
+            // 4. the reference's own quotient for the listed pairs, then the order statistics
+            const int K = (int)(inv2 - inv1);
+            double mine_v[TS_LIST / ST_THREADS];
+#pragma unroll
+            for (int u = 0; u < TS_LIST / ST_THREADS; ++u) {
+                const int q = tid + u * ST_THREADS;
+                mine_v[u] = 0.0;
+                if (q < K) {
+                    const int i = (int)(list[q] >> 16), j = (int)(list[q] & 0xffffu);
+                    mine_v[u] = (t.md[i] - t.md[j]) / (t.ev[i] - t.ev[j]);      // _c_helper.pyx:371-376
+                }
+            }
+            __syncthreads();
+            double *outv = reinterpret_cast<double *>(t.pt);
+#pragma unroll
+            for (int u = 0; u < TS_LIST / ST_THREADS; ++u) {
+                const int q = tid + u * ST_THREADS;
+                if (q < K) outv[q] = mine_v[u];
+            }
+            __syncthreads();
+            tb2_block_select2([&](int i) { return outv[i]; }, PredAll(), K, (int)(k1 - inv1), even,
+                              &v1, &v2, sm);
+            have = true;
+            if (tid == 0) atomicAdd(&g_tb2_counters[5], 1ULL);
+        } else if (tid == 0) {
+            atomicAdd(&g_tb2_counters[6], 1ULL);
+#ifdef TS_DEBUG
+            printf("ts abandon: n=%d Np=%lld k1=%lld bL=%d bH1=%d bH2=%d invL=%lld inv1=%lld inv2=%lld nbuf=%u cum0=%u cumN=%u\n", n, Np, k1, bL, bH1, bH2, invL, inv1, inv2, t.nbuf, t.hist[0], t.hist[TS_SBINS]);
+#endif
+        }
+        __syncthreads();
+    }
     // ---- fast path: fp32 pre-pass picks a bracket [L, H), then ONE exact pass counts
     // the slopes below L and collects those inside; every decision of that pass is
     // exact (a guarded fp32 screen, the true fp64 division whenever a pair is within
     // the guard or inside the bracket), so the selected order statistics are the same
     // doubles np.median sees.  If the bracket misses, fall through.
-    if (hs >= 16 && Np > 4 * TS_ABINS) {
+    if (!have && hs >= 16 && Np > 4 * TS_ABINS) {
         const float lo_f = (float)lo, hi_f = (float)hi;
         const float w_f = (hi_f - lo_f) / (float)TS_ABINS;
         if (hi_f > lo_f && w_f > 0.0f && isfinite(w_f)) {
