@@ -1022,7 +1022,7 @@ __device__ __forceinline__ void ts_pair_of(long long s, int n, int *pi, int *pj)
 // ---------------------------------------------------------------------------
 #define TS_SBINS 1024          // bins of the sample histogram over [lo, hi)
 #define TS_SAMPLES 2048
-#define TS_LIST 2048           // listed (swapped) pairs, u32 each
+#define TS_LIST 4096           // listed (swapped) pairs, u32 each
 #define TS_MAX_PHASES 600
 
 // stable merge sort of (key, id) by key ascending, ids are positions 0..P-1 in ev order; returns
@@ -1179,11 +1179,16 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
     // ---- sort-and-sweep path (see the comment above ts_sort_count) ----
     if (hs >= 16 && n >= 128 && hi > lo) {
         // shared-memory plan: pt (16 KB) = two key arrays for the merge sort, afterwards the
-        // per-element Q (qa) and the pair list (qb), finally the exact slopes; the hist/buf
-        // union = sample CDF (4.1 KB) followed by the two id arrays (4 KB)
+        // per-element Q (qa) and the start of the pair list (qb); the hist/buf union = sample
+        // CDF (4.1 KB, later the rest of the pair list) and, in its last 4 KB, the two id
+        // arrays; the exact slopes finally take pt + union (32 KB = 4096 doubles)
         double *qa = reinterpret_cast<double *>(t.pt), *qb = qa + TS_PAD;
-        unsigned short *pa = reinterpret_cast<unsigned short *>(t.hist + TS_SBINS + 64), *pb = pa + TS_PAD;
+        // ids: the last 4 KB of the union; pair list: from qb (8 KB) on through the union up to
+        // the ids (12 KB) -- it overwrites the sample CDF, which is dead once the listing sweep's
+        // threshold has been picked
+        unsigned short *pa = reinterpret_cast<unsigned short *>(t.buf + (TS_BUF - 512)), *pb = pa + TS_PAD;
         unsigned int *list = reinterpret_cast<unsigned int *>(qb);
+        static_assert(TS_LIST * 4 <= TS_PAD * 8 + (TS_BUF - 512) * 8, "pair list overlaps the id arrays");
         bool ok;
         double M;
         // sample size: about one sample per 24 pairs, 2048 .. 8192
@@ -1215,9 +1220,11 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             __syncthreads();
             const float inv_w = 1.0f / w_f;
             for (int q = tid; q < n_samples; q += ST_THREADS) {
-                const int i = q % n;
-                const int off = 1 + (int)(tb2_mix32((uint32_t)q * 2654435761u + 17u) % (uint32_t)(n - 1));
-                const int j = (i + off) % n;
+                // a pseudo-random pair (i, j != i) without integer division: multiply-shift
+                const uint32_t h1 = tb2_mix32((uint32_t)q * 2654435761u + 17u), h2 = tb2_mix32(h1 ^ 0x9E3779B9u);
+                const int i = (int)(((unsigned long long)h1 * (unsigned long long)n) >> 32);
+                int j = i + 1 + (int)(((unsigned long long)h2 * (unsigned long long)(n - 1)) >> 32);
+                if (j >= n) j -= n;
                 const float sa = __fdividef((float)(t.md[i] - t.md[j]), (float)(t.ev[i] - t.ev[j]));
                 int bin = 0;                                 // bin 0: below lo
                 if (sa >= hi_f) bin = TS_SBINS + 1;          // last: at or above hi (nan lands in bin 0)
@@ -1259,7 +1266,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
         const double ppm = (double)Np / (double)n_samples;       // pairs per sample
         int bL = 0, bH1 = 0, bH2 = 0;
         long long invL = 0, inv1 = 0, inv2 = 0;
-        if (ok) ok = pick((double)k1 / (double)Np - 4.0 * sig, &bL);
+        if (ok) ok = pick((double)k1 / (double)Np - 3.0 * sig, &bL);
         if (ok) {
             // 2. exact count below L: merge sort by Q_L, certainty of the order
             const double TL = thr(bL);
@@ -1324,6 +1331,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
         if (ok) {
             // 4. the reference's own quotient for the listed pairs, then the order statistics
             const int K = (int)(inv2 - inv1);
+            __syncthreads();
             double mine_v[TS_LIST / ST_THREADS];
 #pragma unroll
             for (int u = 0; u < TS_LIST / ST_THREADS; ++u) {
