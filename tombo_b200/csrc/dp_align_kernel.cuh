@@ -12,8 +12,11 @@
 // KLASS 1 is the lean kernel for reads that can only take the static-band path
 // (find_adaptive_base_assignment resquiggle.py:986-989): wavefront engine only, so
 // fewer registers and twice the resident warps of the general kernel.
-template <int KLASS>
-__global__ void __launch_bounds__(ALIGN_WARPS * 32, (KLASS == 1) ? 8 : 4)
+// MINB: resident CTAs per SM the register allocation is bounded for (8 for the lean
+// static-band kernel; 4 or 5 for the general one -- 5 trades a few spills of the register
+// engine's row arrays for a quarter more warps, chosen at launch from measurements)
+template <int KLASS, int MINB = ((KLASS == 1) ? 8 : 4)>
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, MINB)
 k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, int *counter)
 {
     TB2_DYN_SMEM(double, smem);

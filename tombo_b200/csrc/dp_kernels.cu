@@ -1,6 +1,7 @@
 // dp_kernels.cu -- banded DP kernels (sm_100a) and their C-ABI entry points.
 #include "kernels.h"
 #include <algorithm>
+#include <cstdlib>
 
 #include "dp_align_kernel.cuh"
 
@@ -17,7 +18,9 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
         cfg.smem_cells = cap;
         smem = (size_t)ALIGN_WARPS * 2 * cfg.smem_cells * sizeof(double);
     }
-    const int max_blocks = cfg.klass == 1 ? 8 : 4;
+    // general kernel: 4 CTAs (128 registers) or 5 (102 registers) per SM
+    static const int occ2 = [] { const char *e = getenv("TB2_ALIGN2_CTAS"); return (e && atoi(e) == 5) ? 5 : 4; }();
+    const int max_blocks = cfg.klass == 1 ? 8 : occ2;
     int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(max_blocks, (220 * 1024) / std::max<size_t>(smem, 1)));
     int grid = ctx->sm_count * blocks_per_sm;
     const int max_useful = (b.n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS;
@@ -28,7 +31,8 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_GROW].reserve(slots * 2 * (size_t)cfg.grow_cells * sizeof(double) + 8));
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT].reserve(sizeof(int)));
     TB2_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool[SLOT_CNT].p, 0, sizeof(int), ctx->stream));
-    auto kern = cfg.klass == 1 ? k_align<1> : (cfg.klass == 2 ? k_align<2> : k_align<0>);
+    auto kern = cfg.klass == 1 ? k_align<1>
+                : (cfg.klass == 2 ? (occ2 == 5 ? k_align<2, 5> : k_align<2>) : k_align<0>);
     TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
     kern<<<grid, ALIGN_WARPS * 32, smem, ctx->stream>>>(
