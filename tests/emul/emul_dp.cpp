@@ -36,7 +36,7 @@ int emul_align_batch(int klass, int n_reads, const int *cpts, const double *em,
     std::vector<uint32_t> tb_pool(slots * cfg.tb_words + 64);
     std::vector<double> grow_pool(slots * 2 * (size_t)grow_cells + 8);
     int counter = 0;
-    const size_t smem = (size_t)ALIGN_WARPS * 2 * cfg.smem_cells * sizeof(double);
+    const size_t smem = (size_t)ALIGN_WARPS * (2 * (size_t)cfg.smem_cells + TB2_WF_RING) * sizeof(double);
     emul::launch(emul::Idx3{(unsigned)n_blocks, 1, 1}, ALIGN_WARPS * 32, smem, [&]() {
         if (klass == 1) k_align<1>(b, cfg, tb_pool.data(), grow_pool.data(), &counter);
         else if (klass == 2) k_align<2>(b, cfg, tb_pool.data(), grow_pool.data(), &counter);

@@ -29,21 +29,33 @@ __device__ __forceinline__ double tb2_neg_inf()
 __device__ __forceinline__ int tb2_lane() { return threadIdx.x & 31; }
 
 // Correctly rounded a / b for a divisor b that is reused (one k-mer level SD per DP
-// row): y = RN(1/b) once (__drcp_rn), then per quotient one multiply and two
-// residual corrections.  q0 = RN(a*y) is within 2 ulp; the first correction makes
-// q1 faithful; by Markstein's theorem (Markstein 1990; Muller et al., Handbook of
-// Floating-Point Arithmetic, "division by software": y = RN(1/b), q faithful,
-// r = a - b*q exact by FMA  =>  RN(q + r*y) = RN(a/b), barring over/underflow) the
-// second correction returns exactly what the IEEE division of the reference
-// (_c_dynamic_programming.pyx:366) returns.  5 fp64 ops instead of ~25;
+// row).  Once per divisor: y = RN(1/b) (__drcp_rn), e = 1 - b*y (exact in one FMA) and
+// ylo = RN(e*y), so that y + ylo = (1/b)(1 + eps), |eps| <= 2 u^2.  Per quotient four
+// fp64 operations:
+//   t = RN(a*ylo); q0 = RN(a*y + t)   one rounding of (a/b)(1 + 3 u^2): q0 is a/b rounded
+//                                     to nearest unless a/b lies within 3 u^2 of a midpoint,
+//                                     and then still one of its two neighbours (faithful)
+//   r = a - b*q0                      exact by FMA for a faithful q0
+//   q1 = RN(q0 + r*y)                 = RN(a/b) by Markstein's theorem (Markstein 1990;
+//                                     Muller et al., Handbook of Floating-Point Arithmetic,
+//                                     "division by software": y = RN(1/b), q0 faithful),
+//                                     barring over/underflow
+// i.e. exactly what the IEEE division of the reference (_c_dynamic_programming.pyx:366)
+// returns, for 4 operations instead of ~25 (round 1 used RN(a*y) and two corrections: 5).
 // tests/test_div_gpu.py checks it against `/` on 2^31 adversarial and random pairs.
-__device__ __forceinline__ double tb2_div_by(double a, double b, double y)
+struct tb2_rcp { double hi, lo; };
+__device__ __forceinline__ tb2_rcp tb2_rcp_of(double b)
 {
-    double q = __dmul_rn(a, y);
-    double r = __fma_rn(-b, q, a);
-    q = __fma_rn(r, y, q);
-    r = __fma_rn(-b, q, a);
-    return __fma_rn(r, y, q);
+    tb2_rcp y;
+    y.hi = __drcp_rn(b);
+    y.lo = __dmul_rn(__fma_rn(-b, y.hi, 1.0), y.hi);
+    return y;
+}
+__device__ __forceinline__ double tb2_div_by(double a, double b, const tb2_rcp &y)
+{
+    const double q = __fma_rn(a, y.hi, __dmul_rn(a, y.lo));
+    const double r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y.hi, q);
 }
 
 // keyed bijection on [0, n) (mirror of tombo_b200/synthetic.py perm_index):

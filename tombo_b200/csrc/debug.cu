@@ -15,7 +15,7 @@ __device__ __forceinline__ double mk(unsigned long long mant, int e)
                                             (mant & 0xFFFFFFFFFFFFFULL)));
 }
 
-// tb2_div_by(a, b, RN(1/b)) must equal a / b bit for bit
+// tb2_div_by(a, b, tb2_rcp_of(b)) must equal a / b bit for bit
 __global__ void k_div_check(unsigned long long seed, int per_thread, unsigned long long *mism,
                             double *example)
 {
@@ -45,7 +45,7 @@ __global__ void k_div_check(unsigned long long seed, int per_thread, unsigned lo
         }
         if ((r2 >> 40) % 97 == 0) a = 0.0;
         const double want = a / b;
-        const double got = tb2_div_by(a, b, __drcp_rn(b));
+        const double got = tb2_div_by(a, b, tb2_rcp_of(b));
         if (__double_as_longlong(want) != __double_as_longlong(got)) {
             if (bad == 0) { example[0] = a; example[1] = b; example[2] = want; example[3] = got; }
             ++bad;

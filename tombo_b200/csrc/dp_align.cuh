@@ -18,6 +18,7 @@
 struct WarpRes {
     double *smem_rows;    // smem_cap doubles of shared memory
     int smem_cap;
+    double *ring;         // TB2_WF_RING doubles of shared memory (wavefront exchange)
     double *grow;         // optional global row scratch, 2 * grow_cap doubles
     int grow_cap;
     uint32_t *tb;         // packed move scratch
@@ -114,6 +115,7 @@ __device__ __forceinline__ void tb2_pc_defaults(PassCtx &pc, const AlignRead &a,
     pc.mask_shifted = (TB2_MASK_FILL_Z_SCORE - c.z_shift) + c.z_shift;  // resquiggle.py:666,678
     pc.starts = a.starts; pc.tb = wr.tb; pc.dbg_fwd = nullptr; pc.dbg_tb = nullptr;
     pc.buf0 = nullptr; pc.buf1 = nullptr; pc.zbuf = nullptr; pc.cbuf = nullptr; pc.chunk = 0; pc.W = 0;
+    pc.ring = wr.ring;
 }
 
 // static-band forward pass + traceback over rows [0, n_rows) (wavefront engine)

@@ -12,19 +12,19 @@
 // KLASS 1 is the lean kernel for reads that can only take the static-band path
 // (find_adaptive_base_assignment resquiggle.py:986-989): wavefront engine only, so
 // fewer registers and twice the resident warps of the general kernel.
-// MINB: resident CTAs per SM the register allocation is bounded for (8 for the lean
-// static-band kernel; 4 or 5 for the general one -- 5 trades a few spills of the register
-// engine's row arrays for a quarter more warps, chosen at launch from measurements)
-template <int KLASS, int MINB = ((KLASS == 1) ? 8 : 4)>
-__global__ void __launch_bounds__(ALIGN_WARPS * 32, MINB)
+// resident CTAs per SM the register allocation is bounded for: 8 for the lean static-band
+// kernel, 4 for the general one
+template <int KLASS>
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, (KLASS == 1) ? 8 : 4)
 k_align(AlignBatch b, AlignLaunchCfg cfg, uint32_t *tb_pool, double *grow_pool, int *counter)
 {
     TB2_DYN_SMEM(double, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t slot = (size_t)blockIdx.x * ALIGN_WARPS + warp;
     WarpRes wr;
-    wr.smem_rows = smem + (size_t)warp * 2 * cfg.smem_cells;
+    wr.smem_rows = smem + (size_t)warp * (2 * cfg.smem_cells + TB2_WF_RING);
     wr.smem_cap = 2 * cfg.smem_cells;
+    wr.ring = wr.smem_rows + 2 * cfg.smem_cells;
     wr.grow = cfg.grow_cells > 0 ? grow_pool + slot * 2 * (size_t)cfg.grow_cells : nullptr;
     wr.grow_cap = cfg.grow_cells;
     wr.tb = tb_pool + slot * cfg.tb_words;

@@ -8,20 +8,25 @@
 int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cfg_in)
 {
     AlignLaunchCfg cfg = cfg_in;
-    // shared memory: 2 row buffers per warp
+    // shared memory per warp: 2 * smem_cells doubles of rows + the wavefront exchange ring
     const size_t max_smem = 200 * 1024;
-    size_t smem = (size_t)ALIGN_WARPS * 2 * cfg.smem_cells * sizeof(double);
+    const auto smem_of = [](int cells) {
+        return (size_t)ALIGN_WARPS * (2 * (size_t)cells + TB2_WF_RING) * sizeof(double);
+    };
+    size_t smem = smem_of(cfg.smem_cells);
     if (smem > max_smem) {
         // rows that do not fit go to the global row scratch
-        const int cap = (int)(max_smem / (ALIGN_WARPS * 2 * sizeof(double)) / 32) * 32;
+        const int cap = (int)((max_smem / (ALIGN_WARPS * sizeof(double)) - TB2_WF_RING) / 2 / 32) * 32;
         cfg.grow_cells = std::max(cfg.grow_cells, cfg.smem_cells);
         cfg.smem_cells = cap;
-        smem = (size_t)ALIGN_WARPS * 2 * cfg.smem_cells * sizeof(double);
+        smem = smem_of(cfg.smem_cells);
     }
-    // general kernel: 4 CTAs (128 registers) or 5 (102 registers) per SM
-    static const int occ2 = [] { const char *e = getenv("TB2_ALIGN2_CTAS"); return (e && atoi(e) == 5) ? 5 : 4; }();
-    const int max_blocks = cfg.klass == 1 ? 8 : occ2;
-    int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(max_blocks, (220 * 1024) / std::max<size_t>(smem, 1)));
+    // resident CTAs per SM: 8 for the static-band kernel (64 registers), 4 for the general
+    // one (128 registers; a 5-CTA build with 102 registers measured 5 % / 14 % slower on the
+    // configs[2] mix / configs[4], profiles/README.md).  228 KB of shared memory per SM, 1 KB
+    // of it reserved per CTA.
+    const int max_blocks = cfg.klass == 1 ? 8 : 4;
+    int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(max_blocks, (228 * 1024) / (smem + 1024)));
     int grid = ctx->sm_count * blocks_per_sm;
     const int max_useful = (b.n_reads + ALIGN_WARPS - 1) / ALIGN_WARPS;
     if (grid > max_useful) grid = std::max(1, max_useful);
@@ -31,10 +36,11 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_GROW].reserve(slots * 2 * (size_t)cfg.grow_cells * sizeof(double) + 8));
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT].reserve(sizeof(int)));
     TB2_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool[SLOT_CNT].p, 0, sizeof(int), ctx->stream));
-    auto kern = cfg.klass == 1 ? k_align<1>
-                : (cfg.klass == 2 ? (occ2 == 5 ? k_align<2, 5> : k_align<2>) : k_align<0>);
+    auto kern = cfg.klass == 1 ? k_align<1> : (cfg.klass == 2 ? k_align<2> : k_align<0>);
     TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
+    TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           (int)cudaSharedmemCarveoutMaxShared));
     kern<<<grid, ALIGN_WARPS * 32, smem, ctx->stream>>>(
         b, cfg, ctx->pool[SLOT_TB].as<uint32_t>(), ctx->pool[SLOT_GROW].as<double>(),
         ctx->pool[SLOT_CNT].as<int>());
@@ -54,6 +60,7 @@ __global__ void k_banded_forward_dbg(const double *z, const long long *starts64,
     const int lane = tb2_lane();
     WarpRes wr;
     wr.smem_rows = smem; wr.smem_cap = 2 * smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
+    wr.ring = smem + 2 * smem_cells;
     wr.tb = tbp; wr.tb_words = (size_t)nb * TB2_MAX_WPL * 32;
     DpConsts c;
     c.z_shift = 0; c.stay_pen = stay_pen; c.skip_pen = skip_pen; c.mhz = 0; c.winsor = 0;
@@ -61,7 +68,7 @@ __global__ void k_banded_forward_dbg(const double *z, const long long *starts64,
     pc.em = nullptr; pc.n_em = 0; pc.rm = nullptr; pc.rs_ = nullptr; pc.zmat = z;
     pc.mso = 0; pc.msp_start = 0; pc.msp_stop = 0; pc.mask_fill = 0; pc.mask_shifted = 0;
     pc.starts = starts32; pc.tb = tbp; pc.dbg_fwd = fwd; pc.dbg_tb = tb64;
-    pc.zbuf = nullptr; pc.cbuf = nullptr;
+    pc.zbuf = nullptr; pc.cbuf = nullptr; pc.ring = wr.ring;
     int st = TB2_OK;
     pc.W = W; pc.chunk = (W + 31) / 32; pc.buf0 = nullptr; pc.buf1 = nullptr;
     double *rowbuf = tb2_wf_rowbuf(wr, W);
@@ -87,6 +94,7 @@ __global__ void k_adaptive_dbg(double *fwd, long long *tb64, long long *starts64
     const int lane = tb2_lane();
     WarpRes wr;
     wr.smem_rows = smem; wr.smem_cap = 2 * smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
+    wr.ring = smem + 2 * smem_cells;
     wr.tb = tbp; wr.tb_words = (size_t)nb * TB2_MAX_WPL * 32;
     DpConsts c;
     c.z_shift = z_shift; c.stay_pen = stay_pen; c.skip_pen = skip_pen; c.mhz = mhz;
@@ -95,7 +103,7 @@ __global__ void k_adaptive_dbg(double *fwd, long long *tb64, long long *starts64
     pc.em = em; pc.n_em = n_em; pc.rm = rm; pc.rs_ = rs; pc.zmat = nullptr;
     pc.mso = 0; pc.msp_start = 0; pc.msp_stop = 0; pc.mask_fill = mask_fill; pc.mask_shifted = 0;
     pc.starts = starts32; pc.tb = tbp; pc.dbg_fwd = fwd; pc.dbg_tb = tb64;
-    pc.zbuf = nullptr; pc.cbuf = nullptr;
+    pc.zbuf = nullptr; pc.cbuf = nullptr; pc.ring = wr.ring;
     int st = TB2_OK;
     if (!tb2_setup_geom(pc, wr, W)) st = TB2_ERR_CAPACITY;
     const int wpl = tb2_wpl_of(pc.chunk);
@@ -164,7 +172,7 @@ DbgGeom dbg_geom(long long W)
     } else {
         g.smem_cells = 32; g.grow_cells = cells;
     }
-    g.smem_bytes = (size_t)g.smem_cells * 2 * sizeof(double);
+    g.smem_bytes = ((size_t)g.smem_cells * 2 + TB2_WF_RING) * sizeof(double);
     return g;
 }
 }  // namespace
@@ -416,6 +424,7 @@ __global__ void k_single(int mode, const double *em, int n_em, const double *rm,
     const int lane = tb2_lane();
     WarpRes wr;
     wr.smem_rows = smem; wr.smem_cap = 2 * smem_cells; wr.grow = grow; wr.grow_cap = grow_cells;
+    wr.ring = smem + 2 * smem_cells;
     wr.tb = tbp; wr.tb_words = tb_words;
     DpConsts c;
     c.z_shift = p.z_shift; c.stay_pen = p.stay_pen; c.skip_pen = p.skip_pen;

@@ -28,7 +28,8 @@ struct DpConsts {
 struct RowSpec {
     const double *em;    // event means (index e0 + j)
     const double *zrow;  // explicit z-scores of this row (mirror API) or nullptr
-    double mu, sd, inv_sd;  // inv_sd = RN(1 / sd)
+    double mu, sd;
+    tb2_rcp inv_sd;      // reciprocal of sd (tb2_div_by)
     int e0;              // event index of band position 0 (may be negative)
     int lo, hi;          // cells outside [lo, hi) hold maskval
     double maskval;
@@ -304,6 +305,7 @@ struct PassCtx {
     // outputs
     int *starts;             // band event starts per base (global)
     uint32_t *tb;            // packed moves: row r at tb[r * wpl * 32 + w * 32 + lane]
+    double *ring;            // TB2_WF_RING doubles of shared memory (wavefront exchange) or null
     // mirror-API dumps (may be null)
     double *dbg_fwd;         // (n_bases + 1) x W
     long long *dbg_tb;       // (n_bases + 1) x W
@@ -335,7 +337,7 @@ __device__ __noinline__ int tb2_run_rows(const PassCtx &pc, const DpConsts &c, i
         rs.em = pc.em; rs.zrow = nullptr;
         rs.mu = pc.rm ? __ldg(pc.rm + r) : 0.0;
         rs.sd = pc.rs_ ? __ldg(pc.rs_ + r) : 1.0;
-        rs.inv_sd = __drcp_rn(rs.sd);
+        rs.inv_sd = tb2_rcp_of(rs.sd);
         rs.lo = 0; rs.hi = W; rs.maskval = pc.mask_fill;
         int cur_start;
         if (mode == TB2_MODE_ADAPTIVE) {
@@ -527,10 +529,10 @@ __device__ long long tb2_wf_total_words(const int *starts, int r_end, int W)
 }
 
 // shifted z-score of one cell for the wavefront engine.  The divide is the exact
-// reciprocal form (tb2_div_by): inv_sd = RN(1 / sd) once per row.
+// reciprocal form (tb2_div_by): inv_sd = tb2_rcp_of(sd) once per row.
 template <int MODE, bool WIN>
 __device__ __forceinline__ double tb2_wf_z(const double *ep, int j, double mu, double sd,
-                                           double inv_sd, int lo, int hi, double maskval,
+                                           tb2_rcp inv_sd, int lo, int hi, double maskval,
                                            const double *zrow, double zs, double mhz)
 {
     if (MODE == TB2_MODE_EXPLICIT) return zrow[j];
@@ -554,37 +556,50 @@ __device__ __forceinline__ void tb2_rb_st(double *rb, unsigned rb_s, int i, doub
     else rb[i] = v;
 }
 
-// one steady-state step (U = position inside the 16-step group): lane 0 takes the
-// cell above from the row buffer (predicated load at a running address), the tail
-// lane stores its result there; moves enter the word by a funnel shift.
+// move word of one lane over 16 steps: bit q = "step q left the stay candidate behind",
+// bit 16 + q = "its skip candidate beat the diagonal one" (meaningful when bit q is set):
+// stay = 0x, diagonal = 01 (code 2), skip = 11 (code 1).  The steady state sets the two bits
+// straight from its two compare predicates.
+#define TB2_WF_MOVE_BITS(code, q) ((((code) != 0u ? 1u : 0u) << (q)) | (((code) == 1u ? 0x10000u : 0u) << (q)))
+
+// one steady-state step (U = position inside the 16-step group).  Neighbouring lanes
+// exchange the row above through a 48-slot ring in shared memory laid out on the
+// diagonal: lane l stores its cell of step U at slot l + U and lane l + 1 loads it at step
+// U + 1 from (l + 1) - 2 + (U + 1), so both addresses are "per-lane base + 8 * U" and fold
+// into the instruction.  Lane 0 runs its load pointer along the chaining row instead (the
+// tail row of the previous strip) and the tail lane runs its store pointer along it, which
+// removes every predicate and register shuffle of the exchange.  Step 0 of a group takes
+// the cell above by a shuffle (the ring only spans one group).  Within a group slot s is
+// written at step U by lane s - U alone, read by lane s - U + 1 at step U + 1 and
+// overwritten by lane s - U - 1 later in that same step: one __syncwarp() after the load
+// and one after the store order the three (each compiles to a NOP in this converged loop).
 #ifdef TB2_EMUL
 #define TB2_WF_PLD(up, U) if (l0flag) up = tb2_lds(rd_a + 8 * (U));
-#define TB2_WF_PST(nx, U) if (tlflag) tb2_sts(wr_a + 8 * (U), nx);
 #else
 #define TB2_WF_PLD(up, U)                                                                       \
         asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.f64 %0, [%1+%3]; }"    \
                      : "+d"(up) : "r"(rd_a), "r"(l0flag), "n"(8 * (U)));
-#define TB2_WF_PST(nx, U)                                                                       \
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0+%3], %1; }"    \
-                     :: "r"(wr_a), "d"(nx), "r"(tlflag), "n"(8 * (U)) : "memory");
 #endif
 #define TB2_WF_FAST_STEP(U)                                                                     \
     {                                                                                           \
-        double up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);                                     \
-        TB2_WF_PLD(up, U)                                                                       \
+        double up;                                                                              \
+        if ((U) == 0) {                                                                         \
+            up = __shfl_up_sync(TB2_FULL_MASK, xout, 1);                                        \
+            TB2_WF_PLD(up, U)                                                                   \
+        } else up = tb2_lds(rd_a + 8u * (U));                                                   \
+        __syncwarp();                                                                           \
         const double zn = tb2_wf_z<MODE, WIN>(ep + (U) + 1, j + (U) + 1, mu, sd, inv_sd, lo,    \
                                               hi, maskval, nullptr, zs, mhz);                   \
         const double a = (x - stay) + z;                                                        \
         double cc = up_prev + z;                                                                \
-        uint32_t code = 2u;                                                                     \
         const double sk = up - skip;                                                            \
-        if (sk > cc) { cc = sk; code = 1u; }                                                    \
+        if (sk > cc) { cc = sk; cw |= 0x10000u << (U); }                                        \
         double nx = a;                                                                          \
-        if (cc > a) nx = cc; else code = 0u;                                                    \
+        if (cc > a) { nx = cc; cw |= 1u << (U); }                                               \
         up_prev = up;                                                                           \
         x = nx; xout = nx; z = zn;                                                              \
-        cw = __funnelshift_r(cw, code, 2);                                                      \
-        TB2_WF_PST(nx, U)                                                                       \
+        tb2_sts(wr_a + 8u * (U), nx);                                                           \
+        __syncwarp();                                                                           \
     }
 
 template <int MODE, bool DBG, bool WIN, bool RBS>
@@ -596,11 +611,13 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
     const double NEG = tb2_neg_inf();
     const double stay = c.stay_pen, skip = c.skip_pen, zs = c.z_shift, mhz = c.mhz;
     const unsigned rb_s = RBS ? (unsigned)__cvta_generic_to_shared(rowbuf) : 0u;
+    const unsigned ring_s = (RBS && pc.ring) ? (unsigned)__cvta_generic_to_shared(pc.ring) : 0u;
     const double *em = pc.em;
     const int *starts = pc.starts;
     // the steady state is only built for the production modes with the row buffer in
     // shared memory; its first strip reads "the row above row 0" as zeros
-    constexpr bool FAST = RBS && !DBG && MODE != TB2_MODE_EXPLICIT;
+    constexpr bool FAST_T = RBS && !DBG && MODE != TB2_MODE_EXPLICIT;
+    const bool FAST = FAST_T && pc.ring != nullptr;
     if (FAST) {
         for (int jj = lane; jj < W; jj += 32) tb2_rb_st<RBS>(rowbuf, rb_s, jj, 0.0);
         __syncwarp();
@@ -618,7 +635,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
         const int d = start - prev_start;
         const double mu = pc.rm ? __ldg(pc.rm + rr) : 0.0;
         const double sd = pc.rs_ ? __ldg(pc.rs_ + rr) : 1.0;
-        const double inv_sd = __drcp_rn(sd);
+        const tb2_rcp inv_sd = tb2_rcp_of(sd);
         int lo = 0, hi = W;
         double maskval = pc.mask_fill;
         if (MODE == TB2_MODE_MASKED && row_ok) {
@@ -685,7 +702,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
             const int tq = (t - t_begin) & 15;                                                  \
             if (act) {                                                                          \
                 x = nx; xout = nx;                                                              \
-                cw |= code << (2 * tq);                                                         \
+                cw |= TB2_WF_MOVE_BITS(code, tq);                                               \
                 if (is_tail) tb2_rb_st<RBS>(rowbuf, rb_s, j, nx);                               \
             }                                                                                   \
             if (tq == 15 || t == t_end) {                                                       \
@@ -736,7 +753,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
                 }                                                                               \
                 x = nx;                                                                         \
                 xout = nx;                                                                      \
-                cw |= code << (2 * tq);                                                         \
+                cw |= TB2_WF_MOVE_BITS(code, tq);                                               \
                 if (is_tail) tb2_rb_st<RBS>(rowbuf, rb_s, j, nx);                               \
                 if (DBG) {                                                                      \
                     pc.dbg_fwd[(size_t)(r + 1) * W + j] = nx;                                   \
@@ -754,9 +771,12 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
             // ---------- steady state: groups of 16 steps, no band-edge predicates, z one
             // step ahead, one coalesced move-word store per group ----------
             double z = tb2_wf_z<MODE, WIN>(ep, j, mu, sd, inv_sd, lo, hi, maskval, nullptr, zs, mhz);
-            unsigned rd_a = rb_s + 8u * (unsigned)(j + d);     // lane 0: cell above
-            unsigned wr_a = rb_s + 8u * (unsigned)j;           // tail lane: own cell
-            const unsigned l0flag = lane == 0, tlflag = is_tail;
+            // lane 0 loads along the chaining row (cell above), the tail lane stores along
+            // it (own cell); everyone else goes through the ring
+            unsigned rd_a = lane == 0 ? rb_s + 8u * (unsigned)(j + d) : ring_s + 8u * (unsigned)(lane - 2);
+            unsigned wr_a = is_tail ? rb_s + 8u * (unsigned)j : ring_s + 8u * (unsigned)lane;
+            const unsigned rd_inc = lane == 0 ? 128u : 0u, wr_inc = is_tail ? 128u : 0u;
+            const unsigned l0flag = lane == 0;
             uint32_t *tbp = tbs + ((t - t_begin) >> 4) * 32 + lane;
             for (; t + 15 <= t_hi; t += 16) {
                 TB2_WF_FAST_STEP(0) TB2_WF_FAST_STEP(1) TB2_WF_FAST_STEP(2) TB2_WF_FAST_STEP(3)
@@ -764,12 +784,12 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
                 TB2_WF_FAST_STEP(8) TB2_WF_FAST_STEP(9) TB2_WF_FAST_STEP(10) TB2_WF_FAST_STEP(11)
                 TB2_WF_FAST_STEP(12) TB2_WF_FAST_STEP(13) TB2_WF_FAST_STEP(14) TB2_WF_FAST_STEP(15)
                 *tbp = cw;
+                cw = 0u;
                 tbp += 32;
-                rd_a += 128u; wr_a += 128u;
+                rd_a += rd_inc; wr_a += wr_inc;
                 j += 16; ep += 16;
-                // the tail lane's writes to the chaining row trail lane 0's reads by >= 31
-                // cells: a barrier per 16-step group orders every such pair (racecheck-clean)
-                __syncwarp();
+                // (the tail lane's writes to the chaining row trail lane 0's reads by >= 31
+                // cells; the per-step barriers order every such pair)
             }
             cw = 0u;
         }
@@ -869,13 +889,13 @@ __device__ __noinline__ int tb2_tb_seg_wf(const uint32_t *tbw, long long total_w
                 } else {
                     v = tbs[wi * 32 + k];
                 }
-                // a run of stays (code 0) is skipped in one go: highest non-zero move at
-                // or below position q of this word
-                const uint32_t nz = ((v | (v >> 1)) & 0x55555555u) & (0xffffffffu >> (30 - 2 * q));
+                // a run of stays is skipped in one go: highest non-stay move at or below
+                // position q of this word (TB2_WF_MOVE_BITS)
+                const uint32_t nz = (v & 0xffffu) & (0xffffu >> (15 - q));
                 if (nz != 0u) {
-                    const int kq = (31 - __clz(nz)) >> 1;
+                    const int kq = 31 - __clz(nz);
                     bp -= q - kq;
-                    code = (v >> (2 * kq)) & 3u;
+                    code = ((v >> (16 + kq)) & 1u) ? 1u : 2u;
                     break;
                 }
                 bp -= q + 1;

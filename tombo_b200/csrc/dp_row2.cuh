@@ -52,7 +52,7 @@ __host__ __device__ __forceinline__ int tb2_abs_wpr(int ch) { return ch > 16 ? 2
 template <int CH, bool TAIL>
 __device__ __forceinline__ void tb2_abs_walk(const double (&em)[CH], double (&x)[CH], double (&z)[CH],
                                              double pm1, double xc, double mu, double sd,
-                                             double inv_sd, double zs, double mhz, double stay,
+                                             tb2_rcp inv_sd, double zs, double mhz, double stay,
                                              double skip, double maskval, uint32_t vmask,
                                              uint32_t skmask, uint32_t tmask, uint32_t &msk,
                                              uint32_t &mcd)
@@ -129,7 +129,7 @@ __device__ __noinline__ int tb2_adaptive_rows_abs(const PassCtx &pc, const DpCon
         if (lane == 0) pc.starts[r] = cur_start;
         const int d = cur_start - prev_start;
         const double mu = __ldg(pc.rm + r), sd = __ldg(pc.rs_ + r);
-        const double inv_sd = __drcp_rn(sd);
+        const tb2_rcp inv_sd = tb2_rcp_of(sd);
         // the cell left of this lane's chunk in the previous row (diagonal source of cell 0),
         // taken before chunks that left the band are recycled
         const double pm1 = __shfl_sync(TB2_FULL_MASK, x[CH - 1], left_lane);
@@ -347,7 +347,7 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
         if (lane == 0) pc.starts[r] = cur_start;
         const int d = cur_start - prev_start;
         const double mu = __ldg(pc.rm + r), sd = __ldg(pc.rs_ + r);
-        const double inv_sd = __drcp_rn(sd);
+        const tb2_rcp inv_sd = tb2_rcp_of(sd);
         const int c_lo = cur_start / CH;
         const int k = (lane - c_lo) & 31;                  // position of this lane in a pass
         const int last_lane = (c_lo + 31) & 31;            // lane holding a pass's last chunk

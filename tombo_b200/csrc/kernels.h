@@ -92,4 +92,7 @@ static inline size_t tb2_tb_words(long long rows, long long W, long long drift)
     // every mix of the two engines
     return (size_t)(rows * wpl * 32) + tb2_wf_words_bound(rows, W, drift);
 }
+// doubles of shared memory per warp for the wavefront engine's lane-to-lane exchange
+// (dp_row.cuh TB2_WF_FAST_STEP): 32 lanes + 16 steps on the diagonal
+#define TB2_WF_RING 48
 static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }
