@@ -693,7 +693,10 @@ def run_queue_mode(args, rank, world, local, dist):
     from tombo_b200 import _lib, synthetic as syn, multi_gpu as mg
     cfg = CONFIGS[args.workload]
     numa = mg.bind_to_gpu_numa_node(local)
-    ctx = _lib.Context(local)
+    # one context (stream + device pools) per worker thread: while one bucket drains its
+    # last iterations or copies back, the other keeps the SMs and the copy engines busy
+    ctxs = [_lib.Context(local) for _ in range(max(1, args.queue_threads))]
+    ctx = ctxs[0]
     pinned = []
 
     def pin(n, dt):
@@ -704,7 +707,8 @@ def run_queue_mode(args, rank, world, local, dist):
     kmer_ref, cpos, raw, raw_off, seq, seq_off = make_workload(cfg, total, 1, None)
     k = len(kmer_ref[0][0])
     means, sds = syn.kmer_table(kmer_ref)
-    ctx.set_model(means, sds, k, cpos)
+    for c in ctxs:
+        c.set_model(means, sds, k, cpos)
     rp, sp = RP(cfg['aln'], cfg['seg']), RP(cfg['aln'], cfg['seg'], save=True)
     pol = _lib.make_policy(cfg['kind'], subsample_seed=0)
     lens = raw_off[1:] - raw_off[:-1]
@@ -733,13 +737,24 @@ def run_queue_mode(args, rank, world, local, dist):
         barrier(dist)
         t0 = time.perf_counter()
         mine = []
-        while True:
-            i = q.next()
-            if i is None:
-                break
-            r, ro, sq, so = packed[i]
-            results[i] = ctx.resquiggle_batch(r, ro, sq, so, rp, sp, pol)
-            mine.append(i)
+
+        def worker(c):
+            while True:
+                i = q.next()
+                if i is None:
+                    break
+                r, ro, sq, so = packed[i]
+                results[i] = c.resquiggle_batch(r, ro, sq, so, rp, sp, pol)
+                mine.append(i)
+        if len(ctxs) == 1:
+            worker(ctx)
+        else:
+            import threading
+            th = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
         t = time.perf_counter() - t0
         barrier(dist)
         q.close(unlink=(rank == 0))
@@ -766,7 +781,8 @@ def run_queue_mode(args, rank, world, local, dist):
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': cfg['label'] % total + ' -- ONE read set for all GPUs',
                            'queue': 'shared NCCL-free counter in /dev/shm, %d length buckets of '
-                                    '<= %d samples, longest first' % (len(buckets), args.bucket_samples),
+                                    '<= %d samples, longest first, %d worker threads (contexts) per '
+                                    'rank' % (len(buckets), args.bucket_samples, len(ctxs)),
                            'rank_time_min_over_max': t_min / t_max, 'numa': numa,
                            'reads_ok_frac': tot_ok / total,
                            'timing': 'end to end per bucket through tb2_resquiggle_batch, host '
@@ -774,11 +790,12 @@ def run_queue_mode(args, rank, world, local, dist):
                 'e2e': {'value': total * args.steps / t_max, 'unit': 'reads/s',
                         'h2d_bytes_per_step': int(raw.nbytes + seq.nbytes),
                         'd2h_bytes_per_step': int(8 * (nb.sum() * 2 + total * 10))},
-                'gpu_launches': int(ctx.launch_count()), 'clocks': clocks}
+                'gpu_launches': int(sum(c.launch_count() for c in ctxs)), 'clocks': clocks}
         print(json.dumps(line))
     for pa in pinned:
         pa.free()
-    ctx.close()
+    for c in ctxs:
+        c.close()
 
 
 def main():
@@ -798,6 +815,8 @@ def main():
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-int16', action='store_true')
     ap.add_argument('--queue', action='store_true', help='strong scaling over a shared work queue')
+    ap.add_argument('--queue-threads', type=int, default=2,
+                    help='worker threads (one library context each) per rank in --queue mode')
     ap.add_argument('--bucket-samples', type=int, default=60_000_000)
     ap.add_argument('--cpu-leg', default='', help=argparse.SUPPRESS)
     ap.add_argument('--cpu-scale', type=float, default=1.0, help=argparse.SUPPRESS)

@@ -86,3 +86,27 @@ def test_work_queue_and_counter_allreduce_world_size_2(tmp_path):
     got = sorted(outs[0]['mine'] + outs[1]['mine'])
     assert got == list(range(37))                      # every bucket exactly once
     assert outs[0]['tot'] == outs[1]['tot'] == (np.arange(12) * 3).tolist()
+
+
+def test_shared_counter_is_thread_safe(tmp_path):
+    """two worker threads of one rank pull from the same queue object (bench.py --queue
+    --queue-threads 2): every index is handed out exactly once"""
+    import threading
+    from tombo_b200 import multi_gpu as mg
+    q = mg.WorkQueue('tb2_thread_q', 2000, create=True, directory=str(tmp_path))
+    got = [[] for _ in range(4)]
+
+    def worker(k):
+        while True:
+            i = q.next()
+            if i is None:
+                break
+            got[k].append(i)
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    q.close(unlink=True)
+    flat = sorted(i for g in got for i in g)
+    assert flat == list(range(2000))

@@ -12,6 +12,7 @@ import fcntl
 import mmap
 import os
 import struct
+import threading
 
 import numpy as np
 
@@ -103,14 +104,18 @@ class SharedCounter(object):
             os.pwrite(self.fd, struct.pack('<q', 0), 0)
             fcntl.flock(self.fd, fcntl.LOCK_UN)
         self.mm = mmap.mmap(self.fd, 8)
+        self._tlock = threading.Lock()
 
     def fetch_add(self, n=1):
-        fcntl.flock(self.fd, fcntl.LOCK_EX)
-        try:
-            v = struct.unpack_from('<q', self.mm, 0)[0]
-            struct.pack_into('<q', self.mm, 0, v + n)
-        finally:
-            fcntl.flock(self.fd, fcntl.LOCK_UN)
+        # flock excludes other processes; threads of this process share the open file
+        # description (and so the lock), hence the thread lock around it
+        with self._tlock:
+            fcntl.flock(self.fd, fcntl.LOCK_EX)
+            try:
+                v = struct.unpack_from('<q', self.mm, 0)[0]
+                struct.pack_into('<q', self.mm, 0, v + n)
+            finally:
+                fcntl.flock(self.fd, fcntl.LOCK_UN)
         return v
 
     def reset(self, v=0):
