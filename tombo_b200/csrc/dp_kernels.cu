@@ -39,8 +39,11 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
     auto kern = cfg.klass == 1 ? k_align<1> : (cfg.klass == 2 ? k_align<2> : k_align<0>);
     TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
-    TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           (int)cudaSharedmemCarveoutMaxShared));
+    // the static-band kernel needs 8 CTAs x (rows + ring) of shared memory per SM and touches
+    // L1 only for its streaming event loads; the general kernel keeps the default split
+    if (cfg.klass == 1)
+        TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               (int)cudaSharedmemCarveoutMaxShared));
     kern<<<grid, ALIGN_WARPS * 32, smem, ctx->stream>>>(
         b, cfg, ctx->pool[SLOT_TB].as<uint32_t>(), ctx->pool[SLOT_GROW].as<double>(),
         ctx->pool[SLOT_CNT].as<int>());

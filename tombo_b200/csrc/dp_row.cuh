@@ -708,8 +708,10 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
             if (tq == 15 || t == t_end) {                                                       \
                 tbs[((t - t_begin) >> 4) * 32 + lane] = cw;                                     \
                 cw = 0u;                                                                        \
-                __syncwarp();                                                                   \
             }                                                                                   \
+            /* lane 0 reads the chaining row, the tail lane rewrites it a few cells behind  */  \
+            /* (one cell behind in a two-row strip): a barrier per step orders each pair    */  \
+            __syncwarp();                                                                       \
             ++j; ++ep;                                                                          \
         }
         if (lean) {
@@ -764,7 +766,7 @@ __device__ __noinline__ int tb2_wavefront_rows_t(const PassCtx &pc, const DpCons
                 tbs[((t - t_begin) >> 4) * 32 + lane] = cw;                                     \
                 cw = 0u;                                                                        \
             }                                                                                   \
-            if (tq == 15 || t == t_end) __syncwarp();                                           \
+            __syncwarp();                                                                       \
             ++j; ++ep;                                                                          \
         }
         if (lean && t + 15 <= t_hi) {

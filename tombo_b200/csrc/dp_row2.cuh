@@ -177,8 +177,9 @@ __device__ __noinline__ int tb2_adaptive_rows_abs(const PassCtx &pc, const DpCon
             for (int i = 0; i < CH; ++i) {
                 // no early exit: in almost every round some lane right of the path walks its
                 // whole chunk (measured: 11 of 13 steps), a vote per step costs more than it saves
+                // (cells right of the band need no test: z = -inf there, so a = old = -inf, the
+                // "tie" branch rewrites -inf over -inf and x_end does not change)
                 ++n_steps;
-                run = run && ((vmask >> i) & 1u);            // right band edge: the chain ends
                 const double a = (xx - stay) + z[i];
                 const double old = x[i];
                 // stay now wins (ties go to stay).  On an exact tie the walk goes on: the cells
@@ -405,7 +406,6 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
                 double xx = xin;
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
-                    run = run && ((vmask >> i) & 1u);
                     const double a = (xx - stay) + z[i];
                     const double old = x[i];
                     run = run && (a >= old);
