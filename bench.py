@@ -720,11 +720,19 @@ def run_queue_mode(args, rank, world, local, dist):
         r = pin(int(lens[b].sum()), np.float64)
         ro = np.concatenate([[0], np.cumsum(lens[b])]).astype(np.int64)
         so = np.concatenate([[0], np.cumsum(seq_off[b + 1] - seq_off[b])]).astype(np.int64)
-        sq = np.empty(int(so[-1]), dtype=np.uint8)
+        sq = pin(int(so[-1]), np.uint8)
         for j, i in enumerate(b):
             r[ro[j]:ro[j + 1]] = raw[raw_off[i]:raw_off[i + 1]]
             sq[so[j]:so[j + 1]] = seq[seq_off[i]:seq_off[i + 1]]
         packed.append((r, ro, sq, so))
+    # result buffers: pinned, one set per worker, sized for the largest bucket (a bucket's
+    # results are consumed -- here: counted -- before the worker takes the next one)
+    max_n = max(len(b) for b in buckets)
+    max_nb = max(int(nb[b].sum()) for b in buckets)
+    outbufs = [{'segs': pin(max_nb + max_n, np.int64), 'rsrtr': pin(max_n, np.int64),
+                'sv': pin(max_n * 5, np.float64), 'score': pin(max_n, np.float64),
+                'norm_mean': pin(max_nb, np.float64), 'status': pin(max_n, np.int32),
+                'n_iters': pin(max_n, np.int32), 'flags': pin(max_n, np.int32)} for _ in ctxs]
     qname = 'tb2_bench_queue_%s' % os.environ.get('MASTER_PORT', 'solo')
     results = {}
 
@@ -738,19 +746,26 @@ def run_queue_mode(args, rank, world, local, dist):
         t0 = time.perf_counter()
         mine = []
 
-        def worker(c):
+        def worker(c, ob):
             while True:
                 i = q.next()
                 if i is None:
                     break
                 r, ro, sq, so = packed[i]
-                results[i] = c.resquiggle_batch(r, ro, sq, so, rp, sp, pol)
+                n_i, nb_i = len(buckets[i]), int(nb[buckets[i]].sum())
+                out = {'segs': ob['segs'][:nb_i + n_i], 'read_start_rel_to_raw': ob['rsrtr'][:n_i],
+                       'scale_values': ob['sv'][:n_i * 5].reshape(n_i, 5),
+                       'sig_match_score': ob['score'][:n_i], 'norm_mean': ob['norm_mean'][:nb_i],
+                       'status': ob['status'][:n_i], 'n_iters': ob['n_iters'][:n_i],
+                       'flags': ob['flags'][:n_i]}
+                c.resquiggle_batch(r, ro, sq, so, rp, sp, pol, out=out)
+                results[i] = int((out['status'] == 0).sum())
                 mine.append(i)
         if len(ctxs) == 1:
-            worker(ctx)
+            worker(ctx, outbufs[0])
         else:
             import threading
-            th = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
+            th = [threading.Thread(target=worker, args=(c, ob)) for c, ob in zip(ctxs, outbufs)]
             for x in th:
                 x.start()
             for x in th:
@@ -771,7 +786,7 @@ def run_queue_mode(args, rank, world, local, dist):
     t_max = reduce_max(dist, sum(ts))
     t_min = -reduce_max(dist, -sum(ts))
     my_reads = sum(len(buckets[i]) for i in mine)
-    ok = sum(int((results[i]['status'] == 0).sum()) for i in mine)
+    ok = sum(results[i] for i in mine)
     tot_ok = reduce_sum(dist, float(ok))
     if rank == 0:
         line = {'metric': METRIC, 'value': total * args.steps / t_max, 'unit': 'reads/s',

@@ -203,26 +203,20 @@ __device__ __noinline__ int tb2_adaptive_rows_abs(const PassCtx &pc, const DpCon
             tb[((size_t)(r - r_begin) * 2) * 32 + lane] = msk;
             tb[((size_t)(r - r_begin) * 2 + 1) * 32 + lane] = mcd;
         }
-        // ---- first arg-max of the row (c_argmax :186-197): local maximum, warp maximum,
-        // then the first cell (in band order) holding it ----
+        // ---- first arg-max of the row (c_argmax :186-197): first local maximum with its
+        // index, warp maximum, then the smallest event holding it (band order = event order) ----
         double best = x[0];
+        int best_i = 0;
 #pragma unroll
-        for (int i = 1; i < CH; ++i) best = (x[i] > best) ? x[i] : best;
+        for (int i = 1; i < CH; ++i)
+            if (x[i] > best) { best = x[i]; best_i = i; }
         double wbest = best;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const double ob = __shfl_xor_sync(TB2_FULL_MASK, wbest, off);
             wbest = (ob > wbest) ? ob : wbest;
         }
-        int first_i = CH;
-#pragma unroll
-        for (int i = CH - 1; i >= 0; --i) if (x[i] == wbest) first_i = i;
-        // band order = chunk order: lanes rotated so that the band's first chunk comes first
-        const unsigned has = __ballot_sync(TB2_FULL_MASK, first_i < CH);
-        const int rot = c_lo & 31;
-        const unsigned rolled = (has >> rot) | (rot ? (has << (32 - rot)) : 0u);
-        const int win_lane = (__ffs((int)rolled) - 1 + rot) & 31;
-        const int win_e = __shfl_sync(TB2_FULL_MASK, e0 + first_i, win_lane);
+        const int win_e = __reduce_min_sync(TB2_FULL_MASK, (best == wbest) ? e0 + best_i : 0x7fffffff);
         last_argmax = win_e - cur_start;
         // a row of -inf only: the reference's arg-max is position 0
         if (last_argmax < 0 || last_argmax >= W) last_argmax = 0;
