@@ -37,8 +37,10 @@ int tb2_launch_align(tb2_ctx *ctx, const AlignBatch &b, const AlignLaunchCfg &cf
     TB2_CUDA_TRY(ctx, ctx->pool[SLOT_CNT].reserve(sizeof(int)));
     TB2_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool[SLOT_CNT].p, 0, sizeof(int), ctx->stream));
     auto kern = cfg.klass == 1 ? k_align<1> : (cfg.klass == 2 ? k_align<2> : k_align<0>);
+    // (a constant, not this launch's size: contexts launch concurrently from several host
+    // threads and the attribute is per function, not per context)
     TB2_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
+                                           227 * 1024));
     // the static-band kernel needs 8 CTAs x (rows + ring) of shared memory per SM and touches
     // L1 only for its streaming event loads; the general kernel keeps the default split
     if (cfg.klass == 1)

@@ -15,6 +15,8 @@
 #include <cstring>
 #include <memory>
 #include <vector>
+#include <thread>
+#include <atomic>
 
 int tb2_launch_start_attempt(tb2_ctx *ctx, const BatchView &b, int attempt);
 int tb2_launch_end_call(tb2_ctx *ctx, const BatchView &b, int max_iters);
@@ -687,8 +689,51 @@ static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw,
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     };
     const double t00 = now_ms();
-    rc = upload(0);
-    for (int k = 0; k < n_chunks && rc == TB2_OK; ++k) {
+    // Two host threads, one per lane (TB2_PIPELINE_THREADS=1: the single-threaded schedule
+    // below).  Each thread takes every other chunk through upload -> kernels -> download on its
+    // own stream and device pool; the kernels of the two lanes interleave on the device, so
+    // the host round trips between scaling iterations and the tails of one chunk's launches are
+    // filled by the other chunk, and every copy overlaps the other lane's kernels.
+    static const int n_threads = [] { const char *e = getenv("TB2_PIPELINE_THREADS"); return (e && atoi(e) == 1) ? 1 : 2; }();
+    if (n_threads == 2) {
+        int rcs[2] = {TB2_OK, TB2_OK};
+        double st[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        std::atomic<int> failed(0);
+        auto work = [&](int t) {
+          try {
+            tb2_ctx *ln = ctx->lanes[t];
+            if (cudaSetDevice(ctx->device) != cudaSuccess) { rcs[t] = TB2_ERR_CUDA; failed = 1; return; }
+            for (int k = t; k < n_chunks && !failed.load(); k += 2) {
+                int a, b;
+                bounds(k, &a, &b);
+                int r2 = upload(k);
+                ln->read_index_base = a;
+                ln->after_first_launch = nullptr;
+                if (r2 == TB2_OK) r2 = tb2_batch_compute(ln, params, save_params, policy, norm_signal != nullptr);
+                if (r2 == TB2_OK) {
+                    st[t][0] += ln->last_ms_total; st[t][1] += ln->last_ms_dp;
+                    st[t][2] += ln->last_dp_launches; st[t][3] += ln->last_dp_reads;
+                    r2 = tb2_batch_download(ln, segs + base_off[a] + a, read_start_rel_to_raw + a, scale_out + a,
+                                            sig_match_score + a, norm_mean ? norm_mean + base_off[a] : nullptr,
+                                            norm_signal ? norm_signal + raw_off[a] : nullptr, status + a,
+                                            n_iters + a, flags + a);
+                }
+                if (r2 != TB2_OK) { rcs[t] = r2; failed = 1; }
+            }
+          } catch (...) {
+            rcs[t] = TB2_ERR_UNEXPECTED; failed = 1;
+          }
+        };
+        std::thread other(work, 1);
+        work(0);
+        other.join();
+        rc = rcs[0] != TB2_OK ? rcs[0] : rcs[1];
+        for (int t = 0; t < 2; ++t) {
+            ms_total += st[t][0]; ms_dp += st[t][1]; dp_launches += st[t][2]; dp_reads += st[t][3];
+        }
+    } else
+        rc = upload(0);
+    for (int k = 0; n_threads == 1 && k < n_chunks && rc == TB2_OK; ++k) {
         int a, b;
         bounds(k, &a, &b);
         tb2_ctx *ln = ctx->lanes[k & 1];
