@@ -15,8 +15,6 @@
 #include <cstring>
 #include <memory>
 #include <vector>
-#include <thread>
-#include <atomic>
 
 int tb2_launch_start_attempt(tb2_ctx *ctx, const BatchView &b, int attempt);
 int tb2_launch_end_call(tb2_ctx *ctx, const BatchView &b, int max_iters);
@@ -588,11 +586,11 @@ static int batch_download_impl(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_
 // Chunk schedule of the pipelined batch call (host only).  U = one read per resident DP
 // warp of the lean kernel.  Up to 6 U reads go as one batch (returns 1 chunk); larger
 // batches start with short chunks (the first upload is the only exposed one), continue
-// with chunks of 8 U (few launches, short tails) and end with the remainder.
+// with chunks of 6 U (measured best of 6 / 8 / 12 on configs[1]) and end with the remainder.
 static std::vector<int64_t> pipeline_chunk_starts(int sm_count, int64_t n_reads)
 {
     std::vector<int64_t> cs;
-    const int64_t U = (int64_t)std::max(1, sm_count) * 32, CH = 8 * U;
+    const int64_t U = (int64_t)std::max(1, sm_count) * 32, CH = 6 * U;
     int64_t at = 0;
     if (n_reads > 6 * U) {
         const int64_t ramp[2] = {2 * U, 4 * U};
@@ -689,51 +687,13 @@ static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw,
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     };
     const double t00 = now_ms();
-    // Two host threads, one per lane (TB2_PIPELINE_THREADS=1: the single-threaded schedule
-    // below).  Each thread takes every other chunk through upload -> kernels -> download on its
-    // own stream and device pool; the kernels of the two lanes interleave on the device, so
-    // the host round trips between scaling iterations and the tails of one chunk's launches are
-    // filled by the other chunk, and every copy overlaps the other lane's kernels.
-    static const int n_threads = [] { const char *e = getenv("TB2_PIPELINE_THREADS"); return (e && atoi(e) == 1) ? 1 : 2; }();
-    if (n_threads == 2) {
-        int rcs[2] = {TB2_OK, TB2_OK};
-        double st[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-        std::atomic<int> failed(0);
-        auto work = [&](int t) {
-          try {
-            tb2_ctx *ln = ctx->lanes[t];
-            if (cudaSetDevice(ctx->device) != cudaSuccess) { rcs[t] = TB2_ERR_CUDA; failed = 1; return; }
-            for (int k = t; k < n_chunks && !failed.load(); k += 2) {
-                int a, b;
-                bounds(k, &a, &b);
-                int r2 = upload(k);
-                ln->read_index_base = a;
-                ln->after_first_launch = nullptr;
-                if (r2 == TB2_OK) r2 = tb2_batch_compute(ln, params, save_params, policy, norm_signal != nullptr);
-                if (r2 == TB2_OK) {
-                    st[t][0] += ln->last_ms_total; st[t][1] += ln->last_ms_dp;
-                    st[t][2] += ln->last_dp_launches; st[t][3] += ln->last_dp_reads;
-                    r2 = tb2_batch_download(ln, segs + base_off[a] + a, read_start_rel_to_raw + a, scale_out + a,
-                                            sig_match_score + a, norm_mean ? norm_mean + base_off[a] : nullptr,
-                                            norm_signal ? norm_signal + raw_off[a] : nullptr, status + a,
-                                            n_iters + a, flags + a);
-                }
-                if (r2 != TB2_OK) { rcs[t] = r2; failed = 1; }
-            }
-          } catch (...) {
-            rcs[t] = TB2_ERR_UNEXPECTED; failed = 1;
-          }
-        };
-        std::thread other(work, 1);
-        work(0);
-        other.join();
-        rc = rcs[0] != TB2_OK ? rcs[0] : rcs[1];
-        for (int t = 0; t < 2; ++t) {
-            ms_total += st[t][0]; ms_dp += st[t][1]; dp_launches += st[t][2]; dp_reads += st[t][3];
-        }
-    } else
-        rc = upload(0);
-    for (int k = 0; n_threads == 1 && k < n_chunks && rc == TB2_OK; ++k) {
+    // (One host thread drives both lanes.  A thread per lane -- kernels of two chunks resident
+    // side by side, optionally with the persistent DP grids sized to half an SM each -- was
+    // measured 8-10 % slower end to end on configs[1], profiles/README.md call O: the long
+    // persistent DP kernels of one lane stall the short kernels of the other, and nothing is
+    // gained back because the device is already never idle in this schedule.)
+    rc = upload(0);
+    for (int k = 0; k < n_chunks && rc == TB2_OK; ++k) {
         int a, b;
         bounds(k, &a, &b);
         tb2_ctx *ln = ctx->lanes[k & 1];
