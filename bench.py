@@ -498,7 +498,7 @@ def traffic_per_read():
     except Exception:
         return None, 'no capture'
     h = hashlib.sha256()
-    for f in ('dp_row.cuh', 'dp_align.cuh', 'dp_align_kernel.cuh', 'dp_row2.cuh'):
+    for f in ('dp_row.cuh', 'dp_align.cuh', 'dp_align_kernel.cuh', 'dp_row2.cuh', 'common.cuh'):
         p = os.path.join(REPO, 'tombo_b200', 'csrc', f)
         if os.path.exists(p):
             h.update(open(p, 'rb').read())

@@ -159,3 +159,13 @@ def theil_sen(prev_shift, prev_scale, bm, rm, key=0):
                      C.c_int(bm.shape[0]), C.c_double(prev_shift), C.c_double(prev_scale),
                      C.c_uint(key), out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st))
     return st.value, tuple(out.tolist())
+
+
+def select2(values, k):
+    """tb2_block_select2 on the host: (value of rank k, value of rank k + 1)"""
+    L = stage_lib()
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    out = np.zeros(2)
+    L.emul_select2(v.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(v.shape[0]), C.c_int(k),
+                   out.ctypes.data_as(C.POINTER(C.c_double)))
+    return float(out[0]), float(out[1])

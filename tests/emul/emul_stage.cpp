@@ -60,6 +60,18 @@ int emul_theil_sen(const double *bm, const double *rm, int nb, double prev_shift
     return 0;
 }
 
+// tb2_block_select2 (select.cuh) on one array: values of ascending rank k and k + 1
+void emul_select2(const double *v, int n, int k, double *out2)
+{
+    static SelectSmem sm;
+    emul::launch(emul::Idx3{1, 1, 1}, TB2_SEL_THREADS, 0, [&]() {
+        double a = 0, b = 0;
+        auto f = [&](int i) { return v[i]; };
+        tb2_block_select2(f, PredAll(), n, k, true, &a, &b, sm);
+        if (threadIdx.x == 0) { out2[0] = a; out2[1] = b; }
+    });
+}
+
 void emul_ts_counters(unsigned long long *out8, int reset)
 {
     for (int i = 0; i < 8; ++i) out8[i] = g_tb2_counters[i];

@@ -101,3 +101,21 @@ def test_theil_sen_adversarial_inputs_match_oracle(orc):
         assert s1 == s2, (it, n, kind)
         if s1 == 0:
             assert o1[:2] == o2[:2], (it, n, kind)
+
+
+def test_block_select_on_integer_and_tied_values():
+    """the radix select skips every byte in which no two keys differ: integer-valued signal (the
+    int16 DAC dtype: five constant trailing bytes), heavy ties, negative values, all-equal input"""
+    import emul
+    rng = np.random.RandomState(11)
+    cases = [rng.randint(300, 700, size=4150).astype(np.float64),          # DAC-like
+             rng.randint(-5, 6, size=777).astype(np.float64),              # sign changes, many ties
+             np.full(500, 412.0),                                          # all equal
+             np.concatenate([np.full(300, 7.0), rng.randn(5)]),            # one dominant value
+             rng.randn(1000),                                              # generic doubles
+             (rng.randint(0, 8192, size=2000) * 0.25)]                     # few fractional bits
+    for v in cases:
+        sv = np.sort(v)
+        for k in (0, len(v) // 2 - 1, len(v) // 2, len(v) - 2):
+            a, b = emul.select2(v, k)
+            assert a == sv[k] and b == sv[k + 1], (len(v), k, a, b, sv[k], sv[k + 1])

@@ -74,8 +74,11 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
     unsigned int kk = (unsigned int)k;
     const int tid = threadIdx.x;
     if (tid == 0) sm.have2 = 0u;     // published by the barriers below
-    // digits shared by every key need no pass: start below the common leading bytes
+    // digits shared by every key need no pass: start below the common leading bytes, and
+    // skip every later byte in which no two keys differ (integer-valued signal -- the int16
+    // DAC dtype -- has five constant trailing bytes)
     int shift0 = 56;
+    unsigned long long diff_bits = ~0ULL, common_bits = 0ULL;
     {
         unsigned long long all_or = 0, all_and = ~0ULL;
         for (int i = tid; i < n; i += TB2_SEL_THREADS) {
@@ -97,6 +100,7 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
         const unsigned long long diff = all_or ^ all_and;      // bits that differ somewhere
         if (diff == 0ULL) { __syncthreads(); return all_or; }   // all keys equal
         const int top = 63 - __clzll((long long)diff);          // highest differing bit
+        diff_bits = diff; common_bits = all_or;
         shift0 = (top >> 3) << 3;
         if (shift0 < 56) {
             mask = ~0ULL << (shift0 + 8);
@@ -105,6 +109,11 @@ __device__ unsigned long long tb2_block_select_key(F f, Pred pred, int n, int k,
         __syncthreads();
     }
     for (int shift = shift0; shift >= 0; shift -= 8) {
+        if (((diff_bits >> shift) & 0xffULL) == 0ULL) {         // same digit in every key
+            prefix |= common_bits & (0xffULL << shift);
+            mask |= 0xffULL << shift;
+            continue;
+        }
         sm.hist[tid] = 0;
         __syncthreads();
         for (int i = tid; i < n; i += TB2_SEL_THREADS) {

@@ -4,14 +4,14 @@
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r2q_topo.txt 2>&1
 P=29520
-for n in 2 4; do
+for n in ${NS:-2 4}; do
   P=$((P+1))
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $P \
       bench.py --gpus $n --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2q_bench_${n}gpu.json 2> gpurun_out/r2q_bench_${n}gpu.err
 done
 timeout 900 python bench.py --workload mixed --queue --reads 80000 --bucket-samples 16000000 --steps 2 --warmup 1 \
     > gpurun_out/r2q_queue_n1.json 2> gpurun_out/r2q_queue_n1.err
-for n in 2 4; do
+for n in ${NS:-2 4}; do
   P=$((P+1))
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $P \
       bench.py --gpus $n --workload mixed --queue --reads 80000 --bucket-samples 16000000 --steps 2 --warmup 1 \

@@ -20,7 +20,7 @@ def main():
     for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
         tot += float(row[h.index(k)]) * sc[u[h.index(k)]]
     hs = hashlib.sha256()
-    for f in ('dp_row.cuh', 'dp_align.cuh', 'dp_align_kernel.cuh', 'dp_row2.cuh'):
+    for f in ('dp_row.cuh', 'dp_align.cuh', 'dp_align_kernel.cuh', 'dp_row2.cuh', 'common.cuh'):
         p = os.path.join(REPO, 'tombo_b200', 'csrc', f)
         if os.path.exists(p):
             hs.update(open(p, 'rb').read())
