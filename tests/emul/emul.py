@@ -44,7 +44,7 @@ def plan(p, n_em, nb):
     w_main = w_static if is_short else max(sbw, bw)
     smem_cells = L.emul_row_cells(w_main)
     if not is_short and 528 < bw <= 1616:   # three chunks per lane (dp_row2.cuh)
-        smem_cells = max(smem_cells, 3 * (13 if bw <= 1236 else 17) * 32)
+        smem_cells = max(smem_cells, 3 * (13 if bw <= 1236 else 17) * 16)
     elif not is_short and bw > 1616:        # lane-chunk engine rows (dp_row.cuh)
         smem_cells = max(smem_cells, L.emul_row_cells(bw))
     tb = L.emul_tb_words(nb, w_static, n_em)

@@ -265,9 +265,9 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
     // shared-memory lane-chunk engine for wider ones
     const int ach = tb2_abs_chunk(bw);
     // three chunks per lane for bands up to 1616 cells when the warp's shared memory holds
-    // the slabs (2 * 3 * CH * 32 doubles)
+    // the slabs (3 * CH * 32 doubles)
     int mch = ach ? 0 : tb2_abs_ms_chunk_host(bw);
-    if (mch && (wr.smem_cap < 2 * TB2_ABS_MS_SLABS * mch * 32 || !__isShared(wr.smem_rows))) mch = 0;
+    if (mch && (wr.smem_cap < TB2_ABS_MS_SLABS * mch * 32 || !__isShared(wr.smem_rows))) mch = 0;
     int wpl;
     if (ach || mch) {
         pc.W = bw; pc.chunk = 0;

@@ -286,7 +286,11 @@ __device__ __noinline__ int tb2_tb_seg_abs(const uint32_t *tb, const int *starts
 // chunks exactly as in the single-chunk engine (state comes from / goes back to the lane's
 // slab in shared memory: [slab][cell][lane], conflict free), and the chain value leaving the
 // pass's last chunk enters the next pass's first chunk exactly -- no speculation between
-// passes.  Shared memory per warp: 2 * NS * CH * 32 doubles (event means + row values).
+// passes.  Shared memory per warp: NS * CH * 32 doubles of row values.  The event means of a
+// chunk are re-read from global memory in every pass (13-17 loads per lane, 104-136 bytes
+// apart between lanes; the 3-4 KB a pass touches stay in L1 for the ~1000 rows the chunk is
+// inside the band): keeping them in a second slab halved the resident warps (8 per SM) of a
+// kernel that is latency-bound at this band width.
 // ---------------------------------------------------------------------------
 template <int CH, int NS>
 __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const DpConsts &c, int r_begin,
@@ -303,7 +307,7 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
     const double maskval = pc.mask_fill;
     const double *em_g = pc.em;
     const int left_lane = (lane + 31) & 31;
-    double *em_s = st_s + lane, *x_s = st_s + NS * CH * 32 + lane;   // [(slab * CH + i) * 32]
+    double *x_s = st_s + lane;                                       // [(slab * CH + i) * 32]
     int prev_start = pc.starts[r_begin - 1];
     int last_argmax = *argmax_io;
     int c_lo_prev = prev_start / CH;
@@ -325,9 +329,7 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
             const int ch = c_lo_prev + 32 * p + k, sb = ((ch >> 5) % NS) * CH;
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
-                const int e = ch * CH + i;
                 x_s[(sb + i) * 32] = tmp[p][i];
-                em_s[(sb + i) * 32] = (e < n_em) ? __ldg(em_g + e) : 0.0;
             }
         }
         __syncwarp();
@@ -352,7 +354,7 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
         double carry_pm1 = NEG;
         if (c_lo > c_lo_prev) {
             const int cp = c_lo - 1;
-            carry_pm1 = st_s[NS * CH * 32 + ((((cp >> 5) % NS) * CH + CH - 1) * 32) + (cp & 31)];
+            carry_pm1 = st_s[((((cp >> 5) % NS) * CH + CH - 1) * 32) + (cp & 31)];
         }
         double carry_x = NEG;
         double lbest = NEG;
@@ -364,14 +366,8 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
             double em[CH], x[CH], z[CH];
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
-                if (is_new) {
-                    x[i] = NEG;
-                    em[i] = (e0 + i < n_em) ? __ldg(em_g + e0 + i) : 0.0;
-                    em_s[(sb + i) * 32] = em[i];
-                } else {
-                    x[i] = x_s[(sb + i) * 32];
-                    em[i] = em_s[(sb + i) * 32];
-                }
+                em[i] = (e0 + i < n_em) ? __ldg(em_g + e0 + i) : 0.0;
+                x[i] = is_new ? NEG : x_s[(sb + i) * 32];
             }
             double pm1 = __shfl_sync(TB2_FULL_MASK, x[CH - 1], left_lane);
             const double next_pm1 = __shfl_sync(TB2_FULL_MASK, x[CH - 1], last_lane);

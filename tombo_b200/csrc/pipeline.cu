@@ -188,7 +188,8 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
             const long long bw_pairs =
                 tb2_abs_chunk_host(p.bandwidth) != 0 ? (p.bandwidth + 1) / 2
                 : tb2_abs_ms_chunk_host(p.bandwidth) != 0
-                    ? (long long)TB2_ABS_MS_SLABS * tb2_abs_ms_chunk_host(p.bandwidth) * 32
+                    ? std::max<long long>((p.bandwidth + 1) / 2,
+                                          (long long)TB2_ABS_MS_SLABS * tb2_abs_ms_chunk_host(p.bandwidth) * 16)
                     : (p.bandwidth <= 512 ? 2 * bw_cells : bw_cells);
             cl->smem_cells = std::max(cl->smem_cells,
                                       tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2, bw_pairs)));
