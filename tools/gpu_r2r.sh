@@ -17,4 +17,4 @@ timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_dp_gpu
 timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_dp_gpu.py \
     tests/test_pipeline_gpu.py -x -q -k "not large_batch" > gpurun_out/r2r_racecheck.log 2>&1
 tail -3 gpurun_out/r2r_tests.log
-tail -2 gpurun_out/r2r_memcheck.log gpurun_out/r2r_racecheck.log
+tail -n 2 gpurun_out/r2r_memcheck.log; tail -n 2 gpurun_out/r2r_racecheck.log
