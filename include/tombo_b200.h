@@ -257,11 +257,6 @@ int tb2_resquiggle_batch(
  * with sm_count SMs (chunk k = reads [starts_out[k], starts_out[k+1])).  Returns the
  * number of chunks (1 = unpipelined) or a negated TB2_ERR_* code; needs no device. */
 int tb2_pipeline_chunks(int sm_count, int64_t n_reads, int64_t *starts_out, int cap);
-/* The same with the reads weighted by their length (raw_off[n_reads + 1] sample offsets; a
- * read of s samples counts as max(1, s / 4096) unit reads): what tb2_resquiggle_batch
- * does with its own raw_off.  raw_off == NULL: every read weighs 1 (= tb2_pipeline_chunks). */
-int tb2_pipeline_chunks_for(int sm_count, int64_t n_reads, const int64_t *raw_off,
-                            int64_t *starts_out, int cap);
 
 /* The same call in three stages, for callers that keep inputs resident in HBM or
  * overlap transfers themselves: upload (H2D of raw / seq, allocation), compute

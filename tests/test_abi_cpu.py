@@ -111,26 +111,3 @@ def test_pipeline_chunk_schedule_covers_every_read_once():
             assert k >= 2 and sizes[0] == 2 * unit   # short first chunk: its upload is exposed
     assert fn(sm, 10 ** 9, buf, 8) < 0        # capacity is reported, not overrun
     assert fn(sm, -1, buf, 8) < 0
-    # reads weighted by their length: 20000 reads of 2k-20k samples (the configs[2] mix) are
-    # pipelined although they are fewer than 6 * unit reads, 4k-sample reads cut as before
-    fw = lib.tb2_pipeline_chunks_for
-    fw.restype = ctypes.c_int
-    fw.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
-                   ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
-    rng = np.random.RandomState(3)
-    for lens in (rng.randint(2000, 20001, size=20000), np.full(100000, 4096), np.full(2000, 50000),
-                 rng.randint(100, 3000, size=50000)):
-        ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        n = len(lens)
-        k = fw(sm, n, ro.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), buf, 4096)
-        starts = np.array(buf[:k + 1])
-        assert k >= 1 and starts[0] == 0 and starts[-1] == n and np.all(np.diff(starts) > 0)
-        w = np.maximum(1.0, lens / 4096.0)
-        cw = np.add.reduceat(w, starts[:-1])
-        if w.sum() <= 6 * unit:
-            assert k == 1
-        else:
-            assert k >= 2 and cw[0] < 2 * unit + w.max() and np.all(cw <= 6 * unit + w.max())
-    k_mixed = fw(sm, 20000, np.concatenate([[0], np.cumsum(np.full(20000, 11000))]).astype(np.int64)
-                 .ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), buf, 4096)
-    assert k_mixed >= 3

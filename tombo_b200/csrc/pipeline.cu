@@ -585,75 +585,36 @@ static int batch_download_impl(tb2_ctx *ctx, int64_t *segs, int64_t *read_start_
 }
 
 // Chunk schedule of the pipelined batch call (host only).  U = one read per resident DP
-// warp of the lean kernel.  Reads are weighted by their length: a read of s samples counts as
-// max(1, s / 4096) unit reads (the configs[1] read the unit sizes were measured on), so a
-// batch of long reads is cut -- and pipelined -- by the work and the bytes it carries, not by
-// its read count (raw_off == nullptr: every read weighs 1).  Up to 6 U weighted reads go as one
-// batch (returns 1 chunk); larger batches start with short chunks (the first upload is the
-// only exposed one), continue with chunks of 6 U (measured best of 6 / 8 / 12 on configs[1])
-// and end with the remainder.
-static std::vector<int64_t> pipeline_chunk_starts(int sm_count, int64_t n_reads, const int64_t *raw_off)
+// warp of the lean kernel.  Up to 6 U reads go as one batch (returns 1 chunk); larger
+// batches start with short chunks (the first upload is the only exposed one), continue
+// with chunks of 6 U (measured best of 6 / 8 / 12 on configs[1]) and end with the remainder.
+static std::vector<int64_t> pipeline_chunk_starts(int sm_count, int64_t n_reads)
 {
     std::vector<int64_t> cs;
-    const double U = (double)std::max(1, sm_count) * 32.0, CH = 6.0 * U;
-    auto weight = [&](int64_t r) {
-        if (!raw_off) return 1.0;
-        return std::max(1.0, (double)(raw_off[r + 1] - raw_off[r]) / 4096.0);
-    };
-    if (!raw_off) {                                   // unit weights: closed form
-        const int64_t Ui = (int64_t)std::max(1, sm_count) * 32;
-        int64_t at = 0;
-        if (n_reads > 6 * Ui) {
-            const int64_t rampi[2] = {2 * Ui, 4 * Ui};
-            for (int q = 0; q < 2 && n_reads - at > rampi[q]; ++q) { cs.push_back(at); at += rampi[q]; }
-            while (at < n_reads) { cs.push_back(at); at += 6 * Ui; }
-        } else {
-            cs.push_back(0);
-        }
-        cs.push_back(n_reads);
-        return cs;
-    }
-    double total = 0;
-    for (int64_t r = 0; r < n_reads; ++r) total += weight(r);
-    cs.push_back(0);
-    if (total > 6.0 * U) {
-        const double ramp[2] = {2.0 * U, 4.0 * U};
-        double acc = 0, left = total;
-        int q = 0;
-        double target = ramp[0];
-        for (int64_t r = 0; r < n_reads; ++r) {
-            acc += weight(r);
-            if (acc >= target && r + 1 < n_reads) {
-                left -= acc; acc = 0;
-                cs.push_back(r + 1);
-                ++q;
-                // the ramp only continues while more than the next ramp step is left
-                target = (q < 2 && left > ramp[q]) ? ramp[q] : CH;
-                if (q < 2 && !(left > ramp[q])) q = 2;
-            }
-        }
+    const int64_t U = (int64_t)std::max(1, sm_count) * 32, CH = 6 * U;
+    int64_t at = 0;
+    if (n_reads > 6 * U) {
+        const int64_t ramp[2] = {2 * U, 4 * U};
+        for (int q = 0; q < 2 && n_reads - at > ramp[q]; ++q) { cs.push_back(at); at += ramp[q]; }
+        while (at < n_reads) { cs.push_back(at); at += CH; }
+    } else {
+        cs.push_back(0);
     }
     cs.push_back(n_reads);
     return cs;
 }
 
-extern "C" int tb2_pipeline_chunks_for(int sm_count, int64_t n_reads, const int64_t *raw_off,
-                                       int64_t *starts_out, int cap)
+extern "C" int tb2_pipeline_chunks(int sm_count, int64_t n_reads, int64_t *starts_out, int cap)
 {
     if (n_reads < 0 || !starts_out || cap < 2) return -TB2_ERR_INVALID_ARG;
     try {
-        const std::vector<int64_t> cs = pipeline_chunk_starts(sm_count, n_reads, raw_off);
+        const std::vector<int64_t> cs = pipeline_chunk_starts(sm_count, n_reads);
         if ((int)cs.size() > cap) return -TB2_ERR_CAPACITY;
         for (size_t i = 0; i < cs.size(); ++i) starts_out[i] = cs[i];
         return (int)cs.size() - 1;
     } catch (...) {
         return -TB2_ERR_UNEXPECTED;
     }
-}
-
-extern "C" int tb2_pipeline_chunks(int sm_count, int64_t n_reads, int64_t *starts_out, int cap)
-{
-    return tb2_pipeline_chunks_for(sm_count, n_reads, nullptr, starts_out, cap);
 }
 
 static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw, int raw_dtype,
@@ -672,7 +633,7 @@ static int resquiggle_batch_impl(tb2_ctx *ctx, int64_t n_reads, const void *raw,
         !read_start_rel_to_raw || !scale_out || !sig_match_score || !status || !n_iters || !flags ||
         (raw_dtype != 0 && raw_dtype != 1) || n_reads > 0x7ffffff0)
         return TB2_ERR_INVALID_ARG;
-    const std::vector<int64_t> cstart = pipeline_chunk_starts(ctx->sm_count, n_reads, raw_off);
+    const std::vector<int64_t> cstart = pipeline_chunk_starts(ctx->sm_count, n_reads);
     if (cstart.size() <= 2) {
         rc = tb2_batch_upload(ctx, n_reads, raw, raw_dtype, raw_off, seq, seq_off, params, policy);
         if (rc) return rc;
