@@ -66,7 +66,7 @@ CONFIGS = {
                 label='configs[3]: %d synthetic direct-RNA reads/GPU x ~8k samples (270 bases, '
                       '5-mer model), RNA defaults (bw 500, t-test segmentation, stalls) + 5mC '
                       'alt-model per-read LLR + per-position counts, float64 raw'),
-    'c5': dict(kind='DNA', aln=ALN_C5, seg=SEG_DNA, nbases=5555, reads=2000, parity=64,
+    'c5': dict(kind='DNA', aln=ALN_C5, seg=SEG_DNA, nbases=5555, reads=6000, parity=64,
                stall_every=20, stall_extra=11000, cpu_single=2, cpu_pool_per_core=1,
                label='configs[4]: %d synthetic DNA reads/GPU x ~50k samples (5555 bases), '
                      'bandwidth=1200, every 20th read carries an 11k-sample stall (forced '
