@@ -515,6 +515,9 @@ def run_config(name, n_reads, steps, warmup, ctx, rank, local, dist, n_gpus, pin
     cfg = CONFIGS[name]
     rna = cfg['kind'] == 'RNA'
     kmer_ref, cpos, raw, raw_off, seq, seq_off = make_workload(cfg, n_reads, 1 + rank, pin)
+    if os.environ.get('TB2_BENCH_ROUND_RAW'):
+        # diagnostic: integer-valued signal (what the int16 DAC dtype holds) through the f64 path
+        np.round(raw, out=raw)
     k = len(kmer_ref[0][0])
     means, sds = syn.kmer_table(kmer_ref)
     ctx.set_model(means, sds, k, cpos)
