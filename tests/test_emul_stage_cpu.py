@@ -119,3 +119,42 @@ def test_block_select_on_integer_and_tied_values():
         for k in (0, len(v) // 2 - 1, len(v) // 2, len(v) - 2):
             a, b = emul.select2(v, k)
             assert a == sv[k] and b == sv[k + 1], (len(v), k, a, b, sv[k], sv[k + 1])
+
+
+def test_theil_sen_equal_levels_stay_on_the_sort_and_sweep_path(orc):
+    """integer-valued signal (the int16 DAC dtype) makes base means ratios of small integers:
+    equal ev values are the rule, not the exception.  Such pairs have the reference slope 1000.0;
+    the sort-and-sweep path must handle them (same doubles as the oracle) instead of abandoning
+    to the exhaustive path"""
+    import ctypes as C
+    import emul
+    L = emul.stage_lib()
+    rs = np.random.RandomState(5)
+    out = (C.c_ulonglong * 8)()
+    L.emul_ts_counters(out, 1)
+    n_cases = 0
+    for it in range(12):
+        n = int(rs.choice([200, 444, 445, 700]))
+        rm = rs.normal(0, 1.0, n)
+        if it % 3 == 0:       # means of 5-12 integer samples, then an affine map: many exact ties
+            cnt = rs.randint(5, 13, size=n)
+            tot = np.round((rm * 80 + 400) * cnt + rs.normal(0, 12, n) * np.sqrt(cnt))
+            bm = ((tot / cnt) - 400.0) / 80.0
+            bm[rs.randint(0, n, size=n // 10)] = bm[rs.randint(0, n, size=n // 10)]   # forced ties
+        elif it % 3 == 1:     # a 1/16 grid on both axes: ties and identical points
+            bm = np.round((rm * 1.05 + rs.normal(0, 0.15, n)) * 16) / 16
+            rm = np.round(rm * 16) / 16
+        else:                 # a few large tie groups
+            bm = rm * 0.97 + rs.normal(0, 0.1, n)
+            bm[: n // 4] = np.round(bm[: n // 4] * 4) / 4
+        assert len(np.unique(bm)) < n
+        s1, o1 = orc.theil_sen(0.1, 1.2, bm, rm, key=3)
+        s2, o2 = emul.theil_sen(0.1, 1.2, bm, rm, key=3)
+        assert s1 == s2, (it, n)
+        if s1 == 0:
+            assert o1[:2] == o2[:2], (it, n, o1, o2)
+            n_cases += 1
+    L.emul_ts_counters(out, 0)
+    c = list(out)
+    # [5] reads finished by sort-and-sweep, [6] reads that abandoned it
+    assert c[5] >= n_cases - 1 and c[6] <= 1, c

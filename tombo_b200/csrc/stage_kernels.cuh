@@ -1096,11 +1096,13 @@ __device__ long long ts_sweep(unsigned short *perm, const double *q, int n, unsi
 }
 
 // all adjacent gaps of the order `perm` by q exceed the guard (then no pair at all is within it)
-__device__ bool ts_gaps_ok(const unsigned short *perm, const double *q, int n, double g)
+__device__ bool ts_gaps_ok(const unsigned short *perm, const double *q, const double *ev, int n, double g)
 {
     int bad = 0;
-    for (int p = threadIdx.x; p + 1 < n; p += ST_THREADS)
-        bad |= !(q[perm[p + 1]] - q[perm[p]] > g);
+    for (int p = threadIdx.x; p + 1 < n; p += ST_THREADS) {
+        const int x = perm[p], y = perm[p + 1];
+        bad |= !(q[y] - q[x] > g) && (ev[x] != ev[y]);   // equal-ev neighbours are exempt
+    }
     return !__syncthreads_or(bad);
 }
 
@@ -1166,10 +1168,16 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
                 for (int idx = tid; idx < (P >> 1); idx += ST_THREADS) {
                     const int a = ((idx & ~(jj - 1)) << 1) | (idx & (jj - 1)), c = a | jj;
+                    // (ev, md) lexicographic: points of equal ev end up in ascending md, so that
+                    // such a pair -- whose slope the reference defines as 1000.0 -- is never an
+                    // inversion of any Q_T sequence
                     const double ea = t.ev[a], ec = t.ev[c];
-                    if ((ea > ec) == ((a & k) == 0)) {
+                    const double ma = t.md[a], mc = t.md[c];
+                    const bool gt = (ea > ec) || (ea == ec && ma > mc);
+                    const bool ne = (ea != ec) || (ma != mc);
+                    if (ne && (gt == ((a & k) == 0))) {
                         t.ev[a] = ec; t.ev[c] = ea;
-                        const double ma = t.md[a]; t.md[a] = t.md[c]; t.md[c] = ma;
+                        t.md[a] = mc; t.md[c] = ma;
                     }
                 }
                 __syncthreads();
@@ -1177,7 +1185,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
         }
     }
     // ---- sort-and-sweep path (see the comment above ts_sort_count) ----
-    if (hs >= 16 && n >= 128 && hi > lo) {
+    if (hs >= 16 && n >= 128 && hi > lo && hi < 1000.0) {
         // shared-memory plan: pt (16 KB) = two key arrays for the merge sort, afterwards the
         // per-element Q (qa) and the start of the pair list (qb); the hist/buf union = sample
         // CDF (4.1 KB, later the rest of the pair list) and, in its last 4 KB, the two id
@@ -1194,13 +1202,19 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
         // sample size: about one sample per 24 pairs, 2048 .. 8192
         const int n_samples = (int)min(8192LL, max(2048LL, Np / 24));
         {
-            // strictly increasing, finite ev (equal ev: the reference's slope is 1000.0 -- other path)
+            // finite values; ev is non-decreasing after the sort.  Pairs of equal ev (common on
+            // integer-valued signal: base means are ratios of small integers) have the
+            // reference slope 1000.0 for every T: they sit above every threshold this path
+            // uses (hi < 1000 is checked), never count as inversions (sorted by md inside a
+            // tie group), never cross in a sweep (their Q difference does not depend on T) and
+            // are exempt from the guard-gap test (any two elements within the guard are then
+            // joined by a chain of equal-ev neighbours, i.e. are themselves an equal-ev pair)
             int bad = 0;
             double mx = 0.0;
             for (int i = tid; i < n; i += ST_THREADS) {
                 const double e = t.ev[i], m = t.md[i];
                 if (!(fabs(e) < 1e300) || !(fabs(m) < 1e300)) bad = 1;
-                if (i + 1 < n && !(t.ev[i + 1] > e)) bad = 1;
+                if (i + 1 < n && !(t.ev[i + 1] >= e)) bad = 1;
                 mx = fmax(mx, fmax(fabs(e), fabs(m)));
             }
             ok = !__syncthreads_or(bad);
@@ -1225,9 +1239,10 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                 const int i = (int)(((unsigned long long)h1 * (unsigned long long)n) >> 32);
                 int j = i + 1 + (int)(((unsigned long long)h2 * (unsigned long long)(n - 1)) >> 32);
                 if (j >= n) j -= n;
-                const float sa = __fdividef((float)(t.md[i] - t.md[j]), (float)(t.ev[i] - t.ev[j]));
+                const double de = t.ev[i] - t.ev[j];
+                const float sa = __fdividef((float)(t.md[i] - t.md[j]), (float)de);
                 int bin = 0;                                 // bin 0: below lo
-                if (sa >= hi_f) bin = TS_SBINS + 1;          // last: at or above hi (nan lands in bin 0)
+                if (sa >= hi_f || de == 0.0) bin = TS_SBINS + 1;   // last: at or above hi (equal ev: 1000.0)
                 else if (sa >= lo_f) bin = min(TS_SBINS - 1, (int)((sa - lo_f) * inv_w)) + 1;
                 atomicAdd(&t.hist[bin], 1u);
             }
@@ -1282,7 +1297,8 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             unsigned short *ia = pa, *ib = pb;
             invL = ts_sort_count(&ka, &kb, &ia, &ib, P, sm);
             int bad = 0;
-            for (int p2 = tid; p2 + 1 < n; p2 += ST_THREADS) bad |= !(ka[p2 + 1] - ka[p2] > gL);
+            for (int p2 = tid; p2 + 1 < n; p2 += ST_THREADS)
+                bad |= !(ka[p2 + 1] - ka[p2] > gL) && (t.ev[ia[p2]] != t.ev[ia[p2 + 1]]);
             ok = !__syncthreads_or(bad);
             if (ia != pa) for (int i = tid; i < n; i += ST_THREADS) pa[i] = ia[i];
             __syncthreads();
@@ -1304,7 +1320,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
             for (int i = tid; i < n; i += ST_THREADS) qa[i] = __fma_rn(-T1, t.ev[i], t.md[i]);
             __syncthreads();
             const long long sw = ts_sweep(pa, qa, n, nullptr, nullptr, sm);
-            ok = sw >= 0 && ts_gaps_ok(pa, qa, n, 1e-12 * M * (1.0 + fabs(T1)));
+            ok = sw >= 0 && ts_gaps_ok(pa, qa, t.ev, n, 1e-12 * M * (1.0 + fabs(T1)));
             bH1 = bn; inv1 += sw;
             ok = ok && inv1 <= k1;
 #ifdef TS_DEBUG
@@ -1323,7 +1339,7 @@ k_theil_sen(BatchView b, StagePolicy pol, int first_call)
                 if (tid == 0) t.nbuf = 0;
                 __syncthreads();
                 const long long sw = ts_sweep(pa, qa, n, list, &t.nbuf, sm);
-                ok = sw >= 0 && sw <= TS_LIST && ts_gaps_ok(pa, qa, n, 1e-12 * M * (1.0 + fabs(T2)));
+                ok = sw >= 0 && sw <= TS_LIST && ts_gaps_ok(pa, qa, t.ev, n, 1e-12 * M * (1.0 + fabs(T2)));
                 inv2 = inv1 + sw;
                 ok = ok && kT < inv2;
             }
