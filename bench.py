@@ -57,7 +57,7 @@ CONFIGS = {
                label='configs[1]: %d synthetic DNA reads/GPU x ~4k samples (444 bases, 6-mer '
                      'model), bandwidth=200, default start params => static-band path W~748, '
                      'float64 raw'),
-    'mixed': dict(kind='DNA', aln=ALN_MIXED, seg=SEG_DNA, nbases='mixed', reads=20000, parity=512,
+    'mixed': dict(kind='DNA', aln=ALN_MIXED, seg=SEG_DNA, nbases='mixed', reads=40000, parity=512,
                   cpu_single=8, cpu_pool_per_core=4,
                   label='configs[2]-like: %d synthetic DNA reads/GPU, 2k-20k samples (222-2222 '
                         'bases), bandwidth=400 adaptive band + save-bandwidth rescue, float64 raw'),
