@@ -110,3 +110,21 @@ def test_shared_counter_is_thread_safe(tmp_path):
     q.close(unlink=True)
     flat = sorted(i for g in got for i in g)
     assert flat == list(range(2000))
+
+
+def test_length_buckets_tail_is_cut_finer():
+    import numpy as np
+    from tombo_b200 import multi_gpu as mg
+    rng = np.random.RandomState(2)
+    lens = rng.randint(2000, 20001, size=5000)
+    nb = lens // 9
+    plain = mg.length_buckets(lens, nb, target_samples=2000000)
+    guided = mg.length_buckets(lens, nb, target_samples=2000000, tail_fraction=0.25, tail_divisor=4)
+    for b in (plain, guided):
+        assert sorted(np.concatenate(b).tolist()) == list(range(5000))     # every read exactly once
+        assert all(lens[x].sum() <= 2000000 for x in b)
+    assert len(guided) > len(plain)
+    sizes = [int(lens[x].sum()) for x in guided]
+    assert max(sizes[-5:]) <= 500000 and max(sizes[:5]) > 1500000
+    # longest first
+    assert lens[guided[0]].min() >= lens[guided[-1]].max()

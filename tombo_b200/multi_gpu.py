@@ -138,22 +138,30 @@ class SharedCounter(object):
                     pass
 
 
-def length_buckets(raw_lens, n_bases, target_samples, max_reads=65536):
+def length_buckets(raw_lens, n_bases, target_samples, max_reads=65536, tail_fraction=0.0,
+                   tail_divisor=4):
     """Cut a read set into batches of similar shape.  The DP cost of a read is set by its
     events E ~ raw length, its bases B and the bandwidth; with one bandwidth per run, sorting
     by (raw length, bases) groups reads of equal (E, B, bw).  Buckets are runs of the sorted
     order holding at most ``target_samples`` raw samples / ``max_reads`` reads, returned
-    longest first (the expensive buckets are pulled first, the tail is cheap)."""
+    longest first (the expensive buckets are pulled first, the tail is cheap).  The last
+    ``tail_fraction`` of the samples is cut ``tail_divisor`` times finer (guided scheduling:
+    the ranks then finish within a small bucket of each other)."""
     raw_lens = np.asarray(raw_lens, dtype=np.int64)
     order = np.lexsort((np.asarray(n_bases, dtype=np.int64), raw_lens))[::-1]
-    buckets, cur, acc = [], [], 0
+    total = int(raw_lens.sum())
+    tail_from = total - int(total * float(tail_fraction))
+    small = max(1, int(target_samples) // max(1, int(tail_divisor)))
+    buckets, cur, acc, seen = [], [], 0, 0
     for i in order:
         n = int(raw_lens[i])
-        if cur and (acc + n > target_samples or len(cur) >= max_reads):
+        cap = small if seen >= tail_from else target_samples
+        if cur and (acc + n > cap or len(cur) >= max_reads):
             buckets.append(np.array(cur, dtype=np.int64))
             cur, acc = [], 0
         cur.append(int(i))
         acc += n
+        seen += n
     if cur:
         buckets.append(np.array(cur, dtype=np.int64))
     return buckets
