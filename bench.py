@@ -717,7 +717,7 @@ def run_queue_mode(args, rank, world, local, dist):
     lens = raw_off[1:] - raw_off[:-1]
     nb = (seq_off[1:] - seq_off[:-1]) - (k - 1)
     buckets = mg.length_buckets(lens, nb, target_samples=args.bucket_samples,
-                                tail_fraction=args.bucket_tail, tail_divisor=4)
+                                tail_fraction=args.bucket_tail, tail_divisor=args.bucket_tail_div)
     # every rank packs every bucket into pinned buffers (untimed; a loader would emit them)
     packed = []
     for b in buckets:
@@ -800,9 +800,10 @@ def run_queue_mode(args, rank, world, local, dist):
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': cfg['label'] % total + ' -- ONE read set for all GPUs',
                            'queue': 'shared NCCL-free counter in /dev/shm, %d length buckets of '
-                                    '<= %d samples (last %.0f %% of the samples: 4x smaller), longest first, %d worker '
+                                    '<= %d samples (last %.0f %% of the samples: %dx smaller), longest first, %d worker '
                                     'threads (contexts) per rank' % (len(buckets), args.bucket_samples,
-                                                                     100 * args.bucket_tail, len(ctxs)),
+                                                                     100 * args.bucket_tail,
+                                                                     args.bucket_tail_div, len(ctxs)),
                            'rank_time_min_over_max': t_min / t_max, 'numa': numa,
                            'reads_ok_frac': tot_ok / total,
                            'timing': 'end to end per bucket through tb2_resquiggle_batch, host '
@@ -835,9 +836,10 @@ def main():
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-int16', action='store_true')
     ap.add_argument('--queue', action='store_true', help='strong scaling over a shared work queue')
-    ap.add_argument('--bucket-tail', type=float, default=0.25,
-                    help='--queue: fraction of the samples (the shortest reads) cut into 4x smaller buckets')
-    ap.add_argument('--queue-threads', type=int, default=2,
+    ap.add_argument('--bucket-tail', type=float, default=0.15,
+                    help='--queue: fraction of the samples (the shortest reads) cut into smaller buckets')
+    ap.add_argument('--bucket-tail-div', type=int, default=2)
+    ap.add_argument('--queue-threads', type=int, default=4,
                     help='worker threads (one library context each) per rank in --queue mode')
     ap.add_argument('--bucket-samples', type=int, default=60_000_000)
     ap.add_argument('--cpu-leg', default='', help=argparse.SUPPRESS)
