@@ -53,7 +53,7 @@ METRIC = 'resquiggle_reads_per_sec'
 
 CONFIGS = {
     'c1': dict(kind='DNA', aln=ALN_DNA, seg=SEG_DNA, nbases=N_BASES, reads=100000, parity=1024,
-               cpu_single=48, cpu_pool_per_core=64,
+               cpu_single=48, cpu_pool_per_core=96,
                label='configs[1]: %d synthetic DNA reads/GPU x ~4k samples (444 bases, 6-mer '
                      'model), bandwidth=200, default start params => static-band path W~748, '
                      'float64 raw'),
