@@ -53,6 +53,9 @@ CASES = [
     ('abs_ms17_w1500', (4.2, 4.2, 1500, 1500, 20.0, 40, 750, 2500, 250), [2000], 2),
     ('abs_ms17_w1616', (4.2, 4.2, 1616, 1500, 20.0, 40, 750, 2500, 250), [2200], 2),
     ('chunk_engine_w1700', (4.2, 4.2, 1700, 1500, 20.0, 40, 750, 2500, 250), [2200], 2),
+    # a start window (150 events) narrower than the start bases (250): the start score's scratch
+    # no longer fits the row buffer and moves to the (free) move scratch
+    ('start_window_lt_start_bases', (4.2, 4.2, 200, 1500, 20.0, 40, 150, 2500, 250), [700, 300], 2),
 ]
 
 

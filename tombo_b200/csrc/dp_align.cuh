@@ -151,9 +151,14 @@ __device__ __noinline__ int tb2_start_find(const AlignRead &a, const WarpRes &wr
     __syncwarp();
     int st = tb2_static_pass(pc, wr, c, num_events, num_bases, a.read_tb);
     if (st != TB2_OK) return st;
-    // scoring scratch: the (now free) row buffer
+    // scoring scratch (one double per base): the now free row buffer, or -- start windows
+    // narrower than the start bases, never a default -- the move scratch, free as well after
+    // the traceback
     double *t = tb2_wf_rowbuf(wr, num_events);
-    if (num_bases + 1 > num_events) return TB2_ERR_CAPACITY;
+    if (num_bases + 1 > num_events) {
+        t = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(wr.tb) + 7) & ~(uintptr_t)7);
+        if ((size_t)(num_bases + 2) * 2 > wr.tb_words) return TB2_ERR_CAPACITY;
+    }
     int sloc = 0;
     double e = 0;
     if (lane == 0) {
