@@ -98,3 +98,38 @@ def test_device_source_matches_oracle(orc, dna_model, RPcls, name, aln, nbs, kla
             assert np.array_equal(o['segs'], segs)
             assert o['rsrtr'] == rsrtr
             assert o['dbg'][0] == dbg[0]
+
+
+def test_randomized_parameters_match_oracle(orc, dna_model, RPcls):
+    """a seeded sweep over odd parameter combinations (band widths at and around the chunk-width
+    limits, start windows narrower than the start bases, tiny reads): statuses and assignments
+    equal the oracle's.  The sweep this is cut from found the start-score scratch limit."""
+    import emul
+    from tombo_b200 import synthetic as syn
+    kmer_ref, cpos = dna_model
+    means, sds = syn.kmer_table(kmer_ref)
+    rs = np.random.RandomState(77)
+    n_ok = n_fail = 0
+    for it in range(14):
+        bw = int(rs.choice([33, 64, 97, 128, 218, 219, 312, 404, 405, 529, 700]))
+        sbw = int(rs.choice([64, 150, 300, 750, 1000]))
+        snb = int(rs.choice([33, 64, 100, 250]))
+        aln = (float(rs.choice([4.2, 3.0])), float(rs.choice([4.2, 2.0, 6.0])), bw, 1500,
+               float(rs.choice([20.0, 5.0])), int(rs.choice([5, 40])), sbw, int(rs.choice([1500, 2500])), snb)
+        rp = RPcls(aln)
+        nbs = [int(x) for x in rs.randint(20, 1100, size=2)]
+        reads = syn.make_reads(kmer_ref, cpos, len(nbs), nbs, seed0=9000 + it * 10)
+        try:
+            ins = [_events(orc, r, means, sds, rp) for r in reads]
+        except AssertionError:          # the oracle's own stages reject the read (too short)
+            continue
+        res = emul.align_batch(ins, rp, klass=0)
+        for (cp, em, rm, rs_), o in zip(ins, res):
+            st, segs, rsrtr, dbg, epb = orc.find_adaptive_base_assignment(cp, em, rp, rm, rs_)
+            assert o['status'] == st, (it, aln, len(rm), o['status'], st)
+            if st == 0:
+                assert np.array_equal(o['segs'], segs) and o['rsrtr'] == rsrtr, (it, aln, len(rm))
+                n_ok += 1
+            else:
+                n_fail += 1
+    assert n_ok >= 15
