@@ -169,3 +169,37 @@ def select2(values, k):
     L.emul_select2(v.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(v.shape[0]), C.c_int(k),
                    out.ctypes.data_as(C.POINTER(C.c_double)))
     return float(out[0]), float(out[1])
+
+
+def segment(raw, params, num_events, outlier_thresh=5.0, const_scale=None):
+    """k_normalize -> k_cumsum -> k_cpts -> k_event_means on one read ->
+    (status, norm, (shift, scale, lower, upper, outlier_thresh), sorted cpts, event means)"""
+    from tombo_b200 import _lib
+    L = stage_lib()
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    n = raw.shape[0]
+    norm = np.zeros(n)
+    sv = np.zeros(5)
+    cp = np.zeros(num_events + 8, dtype=np.int32)
+    em = np.zeros(num_events + 8)
+    ncp, st = C.c_int(0), C.c_int(0)
+    ps = _lib.params_struct(params)
+    dp = C.POINTER(C.c_double)
+    L.emul_segment(raw.ctypes.data_as(dp), C.c_int(n), C.byref(ps), C.c_int(num_events),
+                   C.c_double(float('nan') if outlier_thresh is None else outlier_thresh),
+                   C.c_double(float('nan') if const_scale is None else const_scale),
+                   norm.ctypes.data_as(dp), sv.ctypes.data_as(dp), cp.ctypes.data_as(C.POINTER(C.c_int)),
+                   C.byref(ncp), em.ctypes.data_as(dp), C.byref(st))
+    k = ncp.value
+    return st.value, norm, tuple(sv.tolist()), cp[:k].astype(np.int64), em[:max(k - 1, 0)]
+
+
+def stalls(raw, stall_cap=64):
+    """k_stalls on one read -> (status, (n, 2) interval array)"""
+    L = stage_lib()
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    ints = np.zeros(2 * stall_cap, dtype=np.int32)
+    k, st = C.c_int(0), C.c_int(0)
+    L.emul_stalls(raw.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(raw.shape[0]), C.c_int(stall_cap),
+                  ints.ctypes.data_as(C.POINTER(C.c_int)), C.byref(k), C.byref(st))
+    return st.value, ints[:2 * min(k.value, stall_cap)].reshape(-1, 2).astype(np.int64), k.value

@@ -60,6 +60,73 @@ int emul_theil_sen(const double *bm, const double *rm, int nb, double prev_shift
     return 0;
 }
 
+// k_normalize -> k_cumsum / k_cpts -> k_event_means on one read (first call of
+// segment_signal resquiggle.py:1052-1117: normalize_raw_signal tombo_stats.py:482-573,
+// c_valid_cpts_w_cap(_t_test) _c_helper.pyx:89-202, c_new_means _c_helper.pyx:59-71)
+int emul_segment(const double *raw, int n, const tb2_params *p, int num_events, double outlier_thresh,
+                 double const_scale, double *norm_out, double *sv_out5, int *cpts_out, int *n_cpts_out,
+                 double *em_out, int *status_out)
+{
+    BatchView b;
+    memset(&b, 0, sizeof(b));
+    long long raw_off[2] = {0, n}, ev_off[2] = {0, (long long)num_events + 8};
+    ReadState st;
+    memset(&st, 0, sizeof(st));
+    st.active = 1; st.status = TB2_OK; st.num_events = num_events;
+    std::vector<double> rawf(raw, raw + n), norm((size_t)n + 8), cs((size_t)n + 16), scores((size_t)n + 8);
+    std::vector<unsigned char> cstate((size_t)2 * n + 1024);
+    std::vector<int> cpts((size_t)num_events + 16);
+    std::vector<double> em((size_t)num_events + 16);
+    b.n_reads = 1; b.max_raw = n; b.raw_off = raw_off; b.ev_off = ev_off;
+    b.rawf = rawf.data(); b.norm = norm.data(); b.cs = cs.data(); b.scores = scores.data();
+    b.cstate = cstate.data(); b.cpts = cpts.data(); b.em = em.data(); b.st = &st;
+    StagePolicy pol;
+    memset(&pol, 0, sizeof(pol));
+    pol.outlier_thresh = outlier_thresh; pol.const_scale = const_scale;
+    emul::launch(emul::Idx3{1, 1, 1}, ST_THREADS, 0, [&]() { k_normalize(b, pol, 1); });
+    if (st.status == TB2_OK) {
+        if (!p->use_t_test_seg)
+            emul::launch(emul::Idx3{1, 1, 1}, CS_WARPS * 32, 0, [&]() { k_cumsum(b, 0); });
+        const long long nw = ((long long)n + 32) / 32;
+        long long words = (4 + std::max(0, (int)p->min_obs_per_base - 1)) * nw;   // tb2_launch_cpts
+        if (words * 4 > 48 * 1024) words = 0;
+        emul::launch(emul::Idx3{1, 1, 1}, ST_THREADS, (size_t)words * 4, [&]() { k_cpts(b, *p, 0, (int)words); });
+    }
+    if (st.status == TB2_OK)
+        emul::launch(emul::Idx3{1, 1, 1}, ST_THREADS, 0, [&]() { k_event_means(b); });
+    for (int i = 0; i < n; ++i) norm_out[i] = norm[i];
+    sv_out5[0] = st.sv.shift; sv_out5[1] = st.sv.scale; sv_out5[2] = st.sv.lower_lim;
+    sv_out5[3] = st.sv.upper_lim; sv_out5[4] = st.sv.outlier_thresh;
+    *n_cpts_out = st.n_cpts;
+    for (int i = 0; i < st.n_cpts && i < num_events + 8; ++i) cpts_out[i] = cpts[i];
+    for (int i = 0; i + 1 < st.n_cpts && i < num_events + 8; ++i) em_out[i] = em[i];
+    *status_out = st.status;
+    return 0;
+}
+
+// k_stalls on one read (identify_stalls, mean-window method, tombo_stats.py:269-368)
+int emul_stalls(const double *raw, int n, int stall_cap, int *ints_out /* 2 * stall_cap */, int *n_out,
+                int *status_out)
+{
+    BatchView b;
+    memset(&b, 0, sizeof(b));
+    long long raw_off[2] = {0, n};
+    ReadState st;
+    memset(&st, 0, sizeof(st));
+    st.active = 1; st.status = TB2_OK;
+    std::vector<double> rawf(raw, raw + n), cs((size_t)n + 16), scores((size_t)n + 8);
+    std::vector<unsigned char> cstate((size_t)2 * n + 1024);
+    std::vector<int> ints((size_t)2 * stall_cap + 8);
+    b.n_reads = 1; b.max_raw = n; b.raw_off = raw_off;
+    b.rawf = rawf.data(); b.cs = cs.data(); b.scores = scores.data(); b.cstate = cstate.data();
+    b.stall_ints = ints.data(); b.stall_cap = stall_cap; b.st = &st;
+    emul::launch(emul::Idx3{1, 1, 1}, ST_THREADS, 0, [&]() { k_stalls(b); });
+    *n_out = st.n_stalls;
+    for (int i = 0; i < 2 * stall_cap; ++i) ints_out[i] = ints[i];
+    *status_out = st.status;
+    return 0;
+}
+
 // tb2_block_select2 (select.cuh) on one array: values of ascending rank k and k + 1
 void emul_select2(const double *v, int n, int k, double *out2)
 {

@@ -158,3 +158,114 @@ def test_theil_sen_equal_levels_stay_on_the_sort_and_sweep_path(orc):
     c = list(out)
     # [5] reads finished by sort-and-sweep, [6] reads that abandoned it
     assert c[5] >= n_cases - 1 and c[6] <= 1, c
+
+
+def _oracle_segment(orc, raw, rp, n_ev, thresh=5.0, const_scale=None):
+    st, norm, sv = orc.normalize_raw_signal(raw, thresh, const_scale=const_scale)
+    if st != 0:
+        return st, None, None, None, None
+    st, cp = orc.valid_cpts_w_cap(norm, rp.min_obs_per_base, rp.running_stat_width, n_ev,
+                                  t_test=rp.use_t_test_seg)
+    if st != 0:
+        return st, norm, sv, None, None
+    cp = np.sort(cp)
+    return 0, norm, sv, cp, orc.new_means(norm, cp)
+
+
+@pytest.mark.parametrize('case', ['dna', 'dna_even_n', 'dna_integer_signal', 'dna_few_levels',
+                                  'rna_t_test', 'const_scale', 'too_many_events', 'flat_signal'])
+def test_segmentation_kernels_match_oracle(orc, dna_model, RPcls, case):
+    """k_normalize (radix-select medians, closed-form clipping medians), k_cumsum, k_cpts (greedy
+    exclusion as a bit-parallel fixed point, ties, N-best cut) and k_event_means on the host
+    emulation: normalised signal, scale values, changepoints and event means equal the oracle's
+    normalize_raw_signal / c_valid_cpts_w_cap(_t_test) / c_new_means bit for bit"""
+    import emul
+    from tombo_b200 import synthetic as syn
+    kmer_ref, cpos = dna_model
+    rna = case == 'rna_t_test'
+    rp = RPcls(seg=(12, 6, 2, 15) if rna else (5, 3, 1, 5), rna=rna)
+    r = syn.make_read(kmer_ref, cpos, 300, 4242)
+    raw = np.asarray(r.raw, dtype=np.float64)
+    const_scale = None
+    if case == 'dna_even_n':
+        raw = raw[:len(raw) - (len(raw) & 1)]
+    elif case == 'dna' and not (len(raw) & 1):
+        raw = raw[:-1]
+    elif case == 'dna_integer_signal':
+        raw = np.round(raw)                       # the int16 DAC dtype: ties everywhere
+    elif case == 'dna_few_levels':
+        raw = np.round(raw / 25.0) * 25.0         # plateaus of equal candidate scores
+    elif case == 'const_scale':
+        const_scale = 61.5
+    elif case == 'flat_signal':
+        raw = np.full(1200, 417.0)                # MAD 0: FloatingPointError in the reference
+    n_ev = max(raw.shape[0] // rp.mean_obs_per_event, 330)
+    if case == 'too_many_events':
+        n_ev = raw.shape[0] // 2                  # more events than the exclusion zones allow
+    so, onorm, osv, ocp, oem = _oracle_segment(orc, raw, rp, n_ev, const_scale=const_scale)
+    se, norm, sv, cp, em = emul.segment(raw, rp, n_ev, const_scale=const_scale)
+    assert (se == 0) == (so == 0), (case, se, so)
+    if so != 0:
+        assert se == so, (case, se, so)
+        return
+    assert np.array_equal(norm, onorm)
+    assert sv[:2] == tuple(osv[:2]) and sv[2:4] == tuple(osv[2:4]), (sv, osv)
+    assert np.array_equal(cp, ocp), (len(cp), len(ocp))
+    assert np.array_equal(em, oem)
+
+
+def test_segmentation_kernels_randomized(orc, dna_model, RPcls):
+    import emul
+    from tombo_b200 import synthetic as syn
+    kmer_ref, cpos = dna_model
+    rs = np.random.RandomState(8)
+    n_ok = 0
+    for it in range(16):
+        rna = it % 4 == 3
+        rp = RPcls(seg=(int(rs.choice([8, 12])), int(rs.choice([4, 6])), 2, 15) if rna
+                   else (int(rs.choice([3, 5, 7])), int(rs.choice([2, 3, 4])), 1, int(rs.choice([4, 5, 8]))), rna=rna)
+        nb = int(rs.choice([40, 100, 270, 444]))
+        raw = np.asarray(syn.make_read(kmer_ref, cpos, nb, 5000 + it).raw, dtype=np.float64)
+        if it % 3 == 1:
+            raw = np.round(raw)
+        n_ev = max(raw.shape[0] // rp.mean_obs_per_event, int(nb * 1.1))
+        so, onorm, osv, ocp, oem = _oracle_segment(orc, raw, rp, n_ev)
+        se, norm, sv, cp, em = emul.segment(raw, rp, n_ev)
+        assert (se == 0) == (so == 0), (it, se, so)
+        if so == 0:
+            assert np.array_equal(norm, onorm) and np.array_equal(cp, ocp) and np.array_equal(em, oem), it
+            assert sv[:4] == tuple(osv[:4])
+            n_ok += 1
+    assert n_ok >= 12
+
+
+def test_stall_detection_kernel_matches_oracle(orc):
+    """k_stalls (mean-window stall detection of direct-RNA reads) on the host emulation:
+    the intervals of identify_stalls, none / one / several stalls, merged neighbours, a read
+    shorter than one window, and an interval buffer that is too small (loud capacity status)"""
+    import emul
+    from tombo_b200 import synthetic as syn
+    kmer_ref, cpos = syn.make_kmer_ref('RNA', 0)
+    rs = np.random.RandomState(4)
+    seen = set()
+    for seed, stall in [(1, None), (2, (100, 1500)), (3, (50, 700)), (4, (200, 3000)), (5, (20, 260))]:
+        raw = np.asarray(syn.make_read(kmer_ref, cpos, 270, seed, stall=stall, kind='RNA').raw,
+                         dtype=np.float64)
+        if seed == 4:          # a second and a third flat stretch, two of them close together
+            raw = np.concatenate([raw[:1500], np.full(600, raw[1500]) + rs.normal(0, 2, 600),
+                                  raw[1500:1700], np.full(500, raw[1700]) + rs.normal(0, 2, 500), raw[1700:]])
+        o = orc.identify_stalls(raw)
+        st, e, k = emul.stalls(raw)
+        assert st == 0 and k == len(o) and np.array_equal(o, e), (seed, o.tolist(), e.tolist())
+        seen.add(len(o))
+    assert 0 in seen and max(seen) >= 2
+    st, e, k = emul.stalls(np.full(100, 400.0))          # shorter than the 350-sample window
+    assert st == 0 and k == 0
+    # capacity: more intervals than the buffer holds is a loud failure, never a truncation
+    many = np.concatenate([np.asarray(syn.make_read(kmer_ref, cpos, 150, 30 + q, stall=(60, 900), kind='RNA').raw,
+                                      dtype=np.float64) for q in range(4)])
+    o = orc.identify_stalls(many)
+    st, e, k = emul.stalls(many, stall_cap=2)
+    assert len(o) > 2 and st == 202
+    st, e, k = emul.stalls(many, stall_cap=64)
+    assert st == 0 and np.array_equal(o, e)
