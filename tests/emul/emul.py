@@ -203,3 +203,19 @@ def stalls(raw, stall_cap=64):
     L.emul_stalls(raw.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(raw.shape[0]), C.c_int(stall_cap),
                   ints.ctypes.data_as(C.POINTER(C.c_int)), C.byref(k), C.byref(st))
     return st.value, ints[:2 * min(k.value, stall_cap)].reshape(-1, 2).astype(np.int64), k.value
+
+
+def finalize(norm, segs, rm, rs, shc, scc, rescale=True):
+    """k_finalize on one read -> (per-base means, re-normalised signal, sig_match_score)"""
+    L = stage_lib()
+    norm, rm, rs = (np.ascontiguousarray(a, dtype=np.float64) for a in (norm, rm, rs))
+    segs = np.ascontiguousarray(segs, dtype=np.int32)
+    nb = rm.shape[0]
+    bm, sig, score = np.zeros(nb), np.zeros(norm.shape[0]), C.c_double(0)
+    dp = C.POINTER(C.c_double)
+    st = L.emul_finalize(norm.ctypes.data_as(dp), C.c_int(norm.shape[0]), segs.ctypes.data_as(C.POINTER(C.c_int)),
+                         C.c_int(nb), rm.ctypes.data_as(dp), rs.ctypes.data_as(dp), C.c_double(shc),
+                         C.c_double(scc), C.c_int(1 if rescale else 0), bm.ctypes.data_as(dp),
+                         sig.ctypes.data_as(dp), C.byref(score))
+    assert st == 0
+    return bm, sig, score.value

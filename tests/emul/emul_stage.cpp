@@ -127,6 +127,31 @@ int emul_stalls(const double *raw, int n, int stall_cap, int *ints_out /* 2 * st
     return 0;
 }
 
+// k_finalize on one read: final re-normalisation, per-base means, sig_match_score
+// (resquiggle.py:1190-1199, get_read_seg_score tombo_stats.py:2327-2338)
+int emul_finalize(const double *norm, int n_norm, const int *segs, int nb, const double *rm,
+                  const double *rs, double shc, double scc, int rescale, double *bm_out,
+                  double *norm_sig_out, double *score_out)
+{
+    BatchView b;
+    memset(&b, 0, sizeof(b));
+    long long raw_off[2] = {0, n_norm}, base_off[2] = {0, nb};
+    ReadState st;
+    memset(&st, 0, sizeof(st));
+    st.active = 1; st.status = TB2_OK; st.rsrtr = 0; st.n_norm = n_norm; st.shc = shc; st.scc = scc;
+    std::vector<double> nv(norm, norm + n_norm), rmv(rm, rm + nb), rsv(rs, rs + nb), bm((size_t)nb + 8),
+        tmp((size_t)nb + 8);
+    std::vector<int> sg(segs, segs + nb + 1);
+    b.n_reads = 1; b.raw_off = raw_off; b.base_off = base_off; b.norm = nv.data(); b.segs = sg.data();
+    b.rm = rmv.data(); b.rs = rsv.data(); b.bm = bm.data(); b.tmp_b = tmp.data(); b.st = &st;
+    StagePolicy pol;
+    memset(&pol, 0, sizeof(pol));
+    pol.skip_seq_scaling = rescale ? 0 : 1;
+    emul::launch(emul::Idx3{1, 1, 1}, ST_THREADS, 0, [&]() { k_finalize(b, pol, 1, bm_out, norm_sig_out); });
+    *score_out = st.score;
+    return st.status;
+}
+
 // tb2_block_select2 (select.cuh) on one array: values of ascending rank k and k + 1
 void emul_select2(const double *v, int n, int k, double *out2)
 {

@@ -269,3 +269,23 @@ def test_stall_detection_kernel_matches_oracle(orc):
     assert len(o) > 2 and st == 202
     st, e, k = emul.stalls(many, stall_cap=64)
     assert st == 0 and np.array_equal(o, e)
+
+
+def test_finalize_kernel_matches_oracle(orc, dna_model, RPcls):
+    """k_finalize: (norm - shift_corr) / scale_corr, per-base means in c_new_means' order and the
+    numpy pairwise-sum mean of |mean - level| / sd"""
+    import emul
+    kmer_ref, cpos = dna_model
+    rp = RPcls(ALN)
+    for nb, seed in [(444, 9100), (129, 9101), (1000, 9102)]:
+        segs, rm, rs, nsig, sv = _dp_segs(orc, kmer_ref, cpos, rp, nb, seed)
+        so, segs = orc.resolve_skipped_bases_with_raw(segs, rm, rs, nsig, rp)    # no empty bases
+        assert so == 0
+        shc, scc = 0.0123, 1.0456
+        for rescale in (True, False):
+            want_sig = (nsig - shc) / scc if rescale else nsig
+            want_bm = orc.new_means(want_sig, segs)
+            want_score = orc.get_read_seg_score(want_bm, rm, rs)
+            bm, sig, score = emul.finalize(nsig, segs, rm, rs, shc, scc, rescale)
+            assert np.array_equal(bm, want_bm) and np.array_equal(sig[:segs[-1]], want_sig[:segs[-1]])
+            assert score == want_score
