@@ -53,8 +53,6 @@ def plan(p, n_em, nb):
         tb = max(tb, L.emul_tb_words(nb, bw, n_em + bw), L.emul_tb_words(snb, sbw, snb),
                  L.emul_tb_words(snb, ssbw, snb))
         grow = max(grow, L.emul_row_cells(ssbw))
-        if 528 < bw <= 1616:                # chunk-transposed event means of the wide-band engine
-            grow = max(grow, L.emul_row_cells((n_em + 4 * 32 * 17 + 64 + 1) // 2))
     return smem_cells, tb, grow, is_short
 
 

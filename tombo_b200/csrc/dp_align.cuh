@@ -346,11 +346,8 @@ __device__ int tb2_align_read(const AlignRead &a, const WarpRes &wr, const tb2_p
         if (st != TB2_OK) return st;
     } else if (mch) {
         // ---- adaptive rows, wide band: three chunks per lane, state in shared memory ----
-        // (the global row scratch is free here: the band rows live in shared memory)
-        const bool grow_free = wr.grow != nullptr && rowbuf != wr.grow;
         st = tb2_adaptive_rows_abs_ms_dyn(mch, pc, c, mask_seq_len, nb, nb, wr.smem_rows, rowbuf,
-                                          tb_chunk, &amax, grow_free ? wr.grow : nullptr,
-                                          grow_free ? 2 * wr.grow_cap : 0);
+                                          tb_chunk, &amax);
         if (st != TB2_OK) return st;
         __syncwarp();
         cur_event = amax + a.starts[nb - 1];

@@ -321,8 +321,6 @@ static void plan_align(const tb2_params &p, long long n_em, long long nb, int *s
         if (n_em >= p.start_save_bw + p.start_n_bases)
             tw = std::max(tw, tb2_tb_words(p.start_n_bases, p.start_save_bw, p.start_n_bases));
         *grow_cells = std::max(*grow_cells, tb2_row_cells(w_rare));
-        if (tb2_abs_chunk_host(p.bandwidth) == 0 && tb2_abs_ms_chunk_host(p.bandwidth) != 0)
-            *grow_cells = std::max(*grow_cells, tb2_row_cells((tb2_abs_ms_emt_doubles(n_em) + 1) / 2));
     }
     *tb_words = std::max(*tb_words, tw);
 }

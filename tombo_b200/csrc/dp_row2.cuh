@@ -290,14 +290,12 @@ __device__ __noinline__ int tb2_tb_seg_abs(const uint32_t *tb, const int *starts
 // chunk are re-read from global memory in every pass (13-17 loads per lane, 104-136 bytes
 // apart between lanes; the 3-4 KB a pass touches stay in L1 for the ~1000 rows the chunk is
 // inside the band): keeping them in a second slab halved the resident warps (8 per SM) of a
-// kernel that is latency-bound at this band width.  When the warp's global row scratch has
-// room, the means are read from a chunk-transposed copy made once per call (see below).
+// kernel that is latency-bound at this band width.
 // ---------------------------------------------------------------------------
 template <int CH, int NS>
 __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const DpConsts &c, int r_begin,
                                                      int r_end, int nb_total, double *st_s,
-                                                     const double *rowbuf, uint32_t *tb, int *argmax_io,
-                                                     double *emt, int emt_cap)
+                                                     const double *rowbuf, uint32_t *tb, int *argmax_io)
 {
     constexpr int WPR = (CH > 16) ? 2 : 1;
     constexpr int NSL = 32 * NS;
@@ -310,22 +308,6 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
     const double *em_g = pc.em;
     const int left_lane = (lane + 31) & 31;
     double *x_s = st_s + lane;                                       // [(slab * CH + i) * 32]
-    // chunk-transposed copy of the event means in global scratch, when the warp has room for
-    // it: element i of chunk c at ((c / 32) * CH + i) * 32 + c % 32, zero beyond the signal --
-    // a pass then loads its CH means with fully coalesced 256-byte requests instead of 32
-    // sectors per load (lanes are CH * 8 bytes apart in the natural layout)
-    const int n_groups = (((n_em + CH - 1) / CH + NSL) >> 5) + 1;
-    const bool use_t = emt != nullptr && (long long)n_groups * CH * 32 <= (long long)emt_cap;
-    if (use_t) {
-        for (int g = 0; g < n_groups; ++g) {
-            const int e0t = (g * 32 + lane) * CH;
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-                emt[(g * CH + i) * 32 + lane] = (e0t + i < n_em) ? __ldg(em_g + e0t + i) : 0.0;
-        }
-        __syncwarp();
-    }
-    const double *emt_l = emt + lane;
     int prev_start = pc.starts[r_begin - 1];
     int last_argmax = *argmax_io;
     int c_lo_prev = prev_start / CH;
@@ -384,8 +366,7 @@ __device__ __noinline__ int tb2_adaptive_rows_abs_ms(const PassCtx &pc, const Dp
             double em[CH], x[CH], z[CH];
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
-                if (use_t) em[i] = emt_l[((ch >> 5) * CH + i) * 32];
-                else em[i] = (e0 + i < n_em) ? __ldg(em_g + e0 + i) : 0.0;
+                em[i] = (e0 + i < n_em) ? __ldg(em_g + e0 + i) : 0.0;
                 x[i] = is_new ? NEG : x_s[(sb + i) * 32];
             }
             double pm1 = __shfl_sync(TB2_FULL_MASK, x[CH - 1], left_lane);
@@ -499,11 +480,11 @@ __device__ __noinline__ int tb2_tb_seg_abs_ms(const uint32_t *tb, const int *sta
 
 __device__ int tb2_adaptive_rows_abs_ms_dyn(int ch, const PassCtx &pc, const DpConsts &c, int r_begin,
                                             int r_end, int nb_total, double *st_s, const double *rowbuf,
-                                            uint32_t *tb, int *amax, double *emt, int emt_cap)
+                                            uint32_t *tb, int *amax)
 {
     switch (ch) {
-    case 13: return tb2_adaptive_rows_abs_ms<13, TB2_ABS_MS_SLABS>(pc, c, r_begin, r_end, nb_total, st_s, rowbuf, tb, amax, emt, emt_cap);
-    case 17: return tb2_adaptive_rows_abs_ms<17, TB2_ABS_MS_SLABS>(pc, c, r_begin, r_end, nb_total, st_s, rowbuf, tb, amax, emt, emt_cap);
+    case 13: return tb2_adaptive_rows_abs_ms<13, TB2_ABS_MS_SLABS>(pc, c, r_begin, r_end, nb_total, st_s, rowbuf, tb, amax);
+    case 17: return tb2_adaptive_rows_abs_ms<17, TB2_ABS_MS_SLABS>(pc, c, r_begin, r_end, nb_total, st_s, rowbuf, tb, amax);
     default: return TB2_ERR_CAPACITY;
     }
 }

@@ -95,7 +95,4 @@ static inline size_t tb2_tb_words(long long rows, long long W, long long drift)
 // doubles of shared memory per warp for the wavefront engine's lane-to-lane exchange
 // (dp_row.cuh TB2_WF_FAST_STEP): 32 lanes + 16 steps on the diagonal
 #define TB2_WF_RING 48
-// doubles of global row scratch the wide-band engine wants for its chunk-transposed copy of
-// n_em event means (dp_row2.cuh): the signal plus one window of 3 x 32 chunks of 17, padded
-static inline long long tb2_abs_ms_emt_doubles(long long n_em) { return n_em + 4 * 32 * 17 + 64; }
 static inline int tb2_row_cells(long long W) { return (int)(((W + 31) / 32) * 32); }

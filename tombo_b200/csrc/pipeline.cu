@@ -193,8 +193,6 @@ void plan_align_batch(const tb2_params &p, const HostBatch &hb, const int64_t *r
                     : (p.bandwidth <= 512 ? 2 * bw_cells : bw_cells);
             cl->smem_cells = std::max(cl->smem_cells,
                                       tb2_row_cells(std::max<long long>((p.start_bw + 1) / 2, bw_pairs)));
-            if (tb2_abs_chunk_host(p.bandwidth) == 0 && tb2_abs_ms_chunk_host(p.bandwidth) != 0)
-                cl->grow_cells = std::max(cl->grow_cells, tb2_row_cells((tb2_abs_ms_emt_doubles(n_em) + 1) / 2));
             cl->tb_words = std::max(cl->tb_words, std::max(tb2_tb_words(nb, p.bandwidth, n_em + p.bandwidth),
                                                            tb2_tb_words(p.start_n_bases, p.start_bw, p.start_n_bases)));
             if (n_em >= p.start_save_bw + p.start_n_bases) {
